@@ -1,0 +1,103 @@
+/*
+ * include/sdf_b200.h -- C ABI of libsdf_b200.so, the B200 (sm_100a) build of sdf_tools' signed-distance-field
+ * hot path.  Plain pointers and sizes only; no C++ / torch / Eigen types cross this boundary.
+ *
+ * The reference has no FFI layer: the hot path is header-only C++ reached through
+ *   sdf_tools::CollisionMapGrid::ExtractSignedDistanceField        include/sdf_tools/collision_map.hpp:680-712
+ *     -> sdf_generation::ExtractSignedDistanceField (grid overload) include/sdf_tools/sdf_generation.hpp:273-286
+ *     -> sdf_generation::ExtractSignedDistanceField<T> (dims)        include/sdf_tools/sdf_generation.hpp:209-271
+ *          = classify (:219-240) + 2 x BuildDistanceField (:95-207, called at :242-243) + combine (:246-268)
+ * and, from Python, through pysdf_tools.CollisionMapGrid.ExtractSignedDistanceField (src/sdf_tools/bindings.cpp:81).
+ * Each entry point below names the reference code it stands in for.  The C++ face that mirrors the reference
+ * signatures (include/sdf_tools_b200/*.hpp) and the Python face (sdf_tools_b200.pysdf_tools) are thin callers
+ * of this ABI; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - memory order of every grid: idx = x*(ny*nz) + y*nz + z, z contiguous (VoxelGrid: utils_3d.py:71-74,
+ *     sdf.cpp:241-245).  mask: 1 byte per voxel, non-zero = FILLED.
+ *   - result: f32 signed distance, negative inside filled voxels, exactly the value the reference stores at
+ *     sdf_generation.hpp:265  (float)(sqrt(d2_filled)*res - sqrt(d2_free)*res), with d2 the exact squared EDT.
+ *   - all functions return SDF_B200_OK (0) or a negative error code; sdf_b200_last_error() gives the text.
+ *     No exceptions cross the ABI.  A context is not thread-safe (the reference is single-threaded too);
+ *     use one context per host thread.  The caller owns every buffer it passes in.
+ *   - there is NO CPU fallback: without a CUDA device sdf_b200_create() fails.
+ */
+#ifndef SDF_B200_H
+#define SDF_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDF_B200_OK 0
+#define SDF_B200_ERR_CUDA (-1)        /* a CUDA runtime call failed (text in last_error)            */
+#define SDF_B200_ERR_ARG (-2)         /* null pointer / negative size / bad argument                 */
+#define SDF_B200_ERR_UNSUPPORTED (-3) /* an axis longer than SDF_B200_MAX_AXIS                       */
+#define SDF_B200_ERR_NOMEM (-4)       /* device or pinned-host allocation failed                     */
+
+#define SDF_B200_MAX_AXIS 2048        /* 32 lanes x 64-bit hull masks per line                       */
+#define SDF_B200_INF 0x40000000       /* |signed d2| sentinel: no voxel of the other polarity exists */
+
+typedef struct sdf_b200_ctx sdf_b200_ctx;
+
+/* Library / device ------------------------------------------------------------------------------------- */
+const char* sdf_b200_version(void);
+int sdf_b200_device_count(void);
+
+/* One context = one device + one stream + its scratch.  `device` is a CUDA ordinal. */
+int sdf_b200_create(sdf_b200_ctx** out, int device);
+void sdf_b200_destroy(sdf_b200_ctx* ctx);
+const char* sdf_b200_last_error(const sdf_b200_ctx* ctx); /* ctx may be NULL: error of the last create() */
+
+/* Use an existing stream (e.g. torch's current stream) for all launches; NULL restores the context's own. */
+int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream);
+int sdf_b200_synchronize(sdf_b200_ctx* ctx);
+
+/* Pinned host buffers for the host-side entry points (optional; any host pointer works, pinned is faster). */
+int sdf_b200_host_alloc(void** out, size_t bytes);
+int sdf_b200_host_free(void* p);
+
+/* Whole path, HOST buffers ----------------------------------------------------------------------------- */
+/* Replaces sdf_generation::ExtractSignedDistanceField<T> (sdf_generation.hpp:209-271) once the caller's
+ * is_filled_fn has been evaluated into `mask` (x->y->z order, :221-227).  out_sdf: nx*ny*nz floats.
+ * out_max / out_min: the extrema pair returned at :269 (max first).  Copies H2D, runs, copies D2H, syncs. */
+int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz,
+                             double resolution, float* out_sdf, double* out_max, double* out_min);
+
+/* Same, straight from CollisionMapGrid storage: cells = nx*ny*nz x {float occupancy; uint32 component}
+ * (collision_map.hpp:20-32).  Applies the is_filled rule of collision_map.hpp:686-709 on the device:
+ * occupancy > 0.5, or == 0.5 when unknown_is_filled. */
+int sdf_b200_build_from_cells(sdf_b200_ctx* ctx, const void* cells, int unknown_is_filled, int64_t nx, int64_t ny,
+                              int64_t nz, double resolution, float* out_sdf, double* out_max, double* out_min);
+
+/* Whole path, DEVICE buffers (asynchronous on the context's stream) ---------------------------------- */
+/* d_mask: nx*ny*nz bytes; d_sdf: nx*ny*nz floats (also used as the in-place int32 work field: no other
+ * scratch is needed).  Extrema are left on the device; fetch them with sdf_b200_get_extrema(). */
+int sdf_b200_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz,
+                          double resolution, float* d_sdf);
+/* Synchronises the stream and returns the (max, min) of the last build on this context (:246-264, :269). */
+int sdf_b200_get_extrema(sdf_b200_ctx* ctx, double* out_max, double* out_min);
+
+/* The is_filled rule alone (collision_map.hpp:686-709): d_cells -> d_mask, n cells, asynchronous. */
+int sdf_b200_pack_cells_device(sdf_b200_ctx* ctx, const void* d_cells, int64_t n, int unknown_is_filled,
+                               uint8_t* d_mask);
+
+/* The two BuildDistanceField results (sdf_generation.hpp:242-243) as ONE signed int32 field, before the
+ * sqrt/resolution combine:  +d2(nearest filled) at free voxels, -d2(nearest free) at filled voxels,
+ * +-SDF_B200_INF where the other polarity does not exist.  For bit-exact integer parity tests. */
+int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz,
+                              int32_t* d_out);
+
+/* Device time of the last build on this context in milliseconds (CUDA events around the launch sequence);
+ * per-kernel times in out_ms[0..3] = {pass 1 (x, binary), pass 2 (y), pass 3 (z + combine), total}. */
+int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4);
+/* Number of kernels the last build launched (for bench.py's gpu_launches). */
+int sdf_b200_last_launches(const sdf_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDF_B200_H */

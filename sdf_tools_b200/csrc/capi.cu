@@ -1,0 +1,280 @@
+// sdf_tools_b200/csrc/capi.cu -- the C ABI of libsdf_b200.so (include/sdf_b200.h) over the kernel launchers.
+// Host orchestration of sdf_generation::ExtractSignedDistanceField<T> (sdf_generation.hpp:209-271):
+//   mask -> K1 (x, binary) -> K2 (y) -> K3 (z + combine) -> f32 field + (max, min).
+#include "../../include/sdf_b200.h"
+#include "edt_kernels.cuh"
+#include "line_hull.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <limits>
+
+struct sdf_b200_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int* d_ext = nullptr;              // [0] max +d2 over free voxels, [1] max d2 over filled voxels
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    int launches = 0;
+    void* d_in = nullptr;  size_t in_bytes = 0;     // staging for the host entry points
+    void* d_mask = nullptr; size_t mask_bytes = 0;
+    void* d_out = nullptr; size_t out_bytes = 0;
+    double res = 1.0;
+    bool built = false;
+    char err[512] = {0};
+};
+
+static char g_create_err[512] = {0};
+
+static int fail(sdf_b200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    char* dst = ctx ? ctx->err : g_create_err;
+    if (e != cudaSuccess) snprintf(dst, 512, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    else snprintf(dst, 512, "%s", what);
+    return code;
+}
+
+#define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(ctx, SDF_B200_ERR_CUDA, what, _e); } while (0)
+
+static int check_dims(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int64_t nz)
+{
+    if (nx < 0 || ny < 0 || nz < 0) return fail(ctx, SDF_B200_ERR_ARG, "negative grid size");
+    if (nx > SDF_B200_MAX_AXIS || ny > SDF_B200_MAX_AXIS || nz > SDF_B200_MAX_AXIS)
+        return fail(ctx, SDF_B200_ERR_UNSUPPORTED, "grid axis longer than SDF_B200_MAX_AXIS (2048)");
+    return SDF_B200_OK;
+}
+
+static int grow(sdf_b200_ctx* ctx, void** p, size_t* have, size_t need)
+{
+    if (need <= *have) return SDF_B200_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SDF_B200_ERR_NOMEM, "cudaMalloc(staging)", e); }
+    *have = need;
+    return SDF_B200_OK;
+}
+
+extern "C" {
+
+const char* sdf_b200_version(void) { return "sdf_b200 0.1 (sm_100a)"; }
+
+int sdf_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sdf_b200_create(sdf_b200_ctx** out, int device)
+{
+    sdf_b200_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create: no CUDA device (this library has no CPU fallback)", e);
+    }
+    if (device < 0 || device >= n) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create: bad device ordinal");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, SDF_B200_ERR_CUDA, "cudaSetDevice", e);
+    ctx = new sdf_b200_ctx();
+    ctx->device = device;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_ext, 2 * sizeof(int))) != cudaSuccess) {
+        fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create: stream/alloc", e);
+        delete ctx;
+        return SDF_B200_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SDF_B200_OK;
+}
+
+void sdf_b200_destroy(sdf_b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->d_ext) cudaFree(ctx->d_ext);
+    if (ctx->d_in) cudaFree(ctx->d_in);
+    if (ctx->d_mask) cudaFree(ctx->d_mask);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* sdf_b200_last_error(const sdf_b200_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SDF_B200_OK;
+}
+
+int sdf_b200_synchronize(sdf_b200_ctx* ctx)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+    return SDF_B200_OK;
+}
+
+int sdf_b200_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return SDF_B200_ERR_ARG;
+    *out = nullptr;
+    if (bytes == 0) return SDF_B200_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SDF_B200_ERR_NOMEM, "cudaHostAlloc", e); }
+    return SDF_B200_OK;
+}
+
+int sdf_b200_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return SDF_B200_ERR_CUDA; }
+    return SDF_B200_OK;
+}
+
+// mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in place in d_field
+static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz, double res,
+                      int32_t* d_field, bool final_pass)
+{
+    cudaStream_t st = ctx->stream;
+    ctx->launches = 0;
+    ctx->timed = false;
+    CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
+    if (nx * ny * nz == 0) { ctx->built = true; ctx->res = res; return SDF_B200_OK; }
+    CK(cudaEventRecord(ctx->ev[0], st), "event");
+    CK(sdfb200::launch_binary_x(d_mask, d_field, (int)nx, ny * nz, st), "launch binary_x");
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[1], st), "event");
+    if (ny > 1) {
+        CK(sdfb200::launch_hull_strided(d_field, (int)ny, nz, nz, nx, ny * nz, st), "launch hull_strided");
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], st), "event");
+    CK(sdfb200::launch_hull_contig(d_field, (int)nz, nx * ny, final_pass, res, ctx->d_ext, st), "launch hull_contig");
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[3], st), "event");
+    ctx->timed = true;
+    ctx->built = final_pass;
+    ctx->res = res;
+    return SDF_B200_OK;
+}
+
+int sdf_b200_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz,
+                          double resolution, float* d_sdf)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz);
+    if (rc) return rc;
+    if (nx * ny * nz > 0 && (!d_mask || !d_sdf)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return run_passes(ctx, d_mask, nx, ny, nz, resolution, reinterpret_cast<int32_t*>(d_sdf), true);
+}
+
+int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz,
+                              int32_t* d_out)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz);
+    if (rc) return rc;
+    if (nx * ny * nz > 0 && (!d_mask || !d_out)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return run_passes(ctx, d_mask, nx, ny, nz, 1.0, d_out, false);
+}
+
+int sdf_b200_get_extrema(sdf_b200_ctx* ctx, double* out_max, double* out_min)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    if (!ctx->built) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_get_extrema: no finished build on this context");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    const double inf = std::numeric_limits<double>::infinity();
+    // distance = sqrt(d2_filled)*res - sqrt(d2_free)*res, one term being 0 (sdf_generation.hpp:254-256);
+    // sqrt is monotone, so the extrema of the f64 value sit at the per-polarity maxima of d2.
+    auto dist = [&](int m) { return (m >= SDF_B200_INF) ? inf : sqrt((double)m) * ctx->res; };
+    const bool any_free = h[0] > 0, any_filled = h[1] > 0;
+    const double mx = any_free ? dist(h[0]) : -inf;                 // no free voxel: every value is -inf (or grid empty)
+    const double mn = any_filled ? -dist(h[1]) : inf;               // no filled voxel: every value is +inf (or grid empty)
+    if (out_max) *out_max = mx;
+    if (out_min) *out_min = mn;
+    return SDF_B200_OK;
+}
+
+int sdf_b200_pack_cells_device(sdf_b200_ctx* ctx, const void* d_cells, int64_t n, int unknown_is_filled,
+                               uint8_t* d_mask)
+{
+    if (!ctx || n < 0) return SDF_B200_ERR_ARG;
+    if (n > 0 && (!d_cells || !d_mask)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(sdfb200::launch_pack_cells(d_cells, n, unknown_is_filled, d_mask, ctx->stream), "launch pack_cells");
+    return SDF_B200_OK;
+}
+
+static int build_host_common(sdf_b200_ctx* ctx, const void* h_in, size_t in_bytes, bool is_cells, int unknown_is_filled,
+                             int64_t nx, int64_t ny, int64_t nz, double res, float* out_sdf, double* out_max,
+                             double* out_min)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz);
+    if (rc) return rc;
+    const int64_t N = nx * ny * nz;
+    if (N > 0 && (!h_in || !out_sdf)) return fail(ctx, SDF_B200_ERR_ARG, "null host pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    if (N > 0) {
+        if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)N))) return rc;
+        if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+        if (is_cells) {
+            if ((rc = grow(ctx, &ctx->d_in, &ctx->in_bytes, in_bytes))) return rc;
+            CK(cudaMemcpyAsync(ctx->d_in, h_in, in_bytes, cudaMemcpyHostToDevice, st), "H2D cells");
+            CK(sdfb200::launch_pack_cells(ctx->d_in, N, unknown_is_filled, (uint8_t*)ctx->d_mask, st), "launch pack_cells");
+        } else {
+            CK(cudaMemcpyAsync(ctx->d_mask, h_in, in_bytes, cudaMemcpyHostToDevice, st), "H2D mask");
+        }
+    }
+    rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, nx, ny, nz, res, (int32_t*)ctx->d_out, true);
+    if (rc) return rc;
+    if (is_cells && N > 0) ctx->launches++;
+    if (N > 0) CK(cudaMemcpyAsync(out_sdf, ctx->d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, st), "D2H sdf");
+    return sdf_b200_get_extrema(ctx, out_max, out_min);
+}
+
+int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz,
+                             double resolution, float* out_sdf, double* out_max, double* out_min)
+{
+    return build_host_common(ctx, mask, (size_t)(nx * ny * nz), false, 0, nx, ny, nz, resolution, out_sdf, out_max, out_min);
+}
+
+int sdf_b200_build_from_cells(sdf_b200_ctx* ctx, const void* cells, int unknown_is_filled, int64_t nx, int64_t ny,
+                              int64_t nz, double resolution, float* out_sdf, double* out_max, double* out_min)
+{
+    return build_host_common(ctx, cells, (size_t)(nx * ny * nz) * 8, true, unknown_is_filled, nx, ny, nz, resolution,
+                             out_sdf, out_max, out_min);
+}
+
+int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4)
+{
+    if (!ctx || !out_ms4) return SDF_B200_ERR_ARG;
+    if (!ctx->timed) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_last_timing: nothing timed");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaEventSynchronize(ctx->ev[3]), "event sync");
+    for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&out_ms4[i], ctx->ev[i], ctx->ev[i + 1]), "elapsed");
+    CK(cudaEventElapsedTime(&out_ms4[3], ctx->ev[0], ctx->ev[3]), "elapsed");
+    return SDF_B200_OK;
+}
+
+int sdf_b200_last_launches(const sdf_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/sdf_b200.h), against the CPU oracle.
+
+Parity protocol:
+  P0  sign of the SDF == occupancy, bit-exact at every voxel
+  P1  integer signed d^2 == exact-EDT oracle, bit-exact at every voxel
+  P2  f32 SDF == oracle f32 SDF bit-for-bit (same f64 sqrt*res, same cast), hence <= 1e-5 relative to the
+      reference wherever the reference's propagation found the true nearest voxel
+  P3  where the reference (oracle/_ref) differs, |reference| >= |gpu| (its propagation only over-estimates)
+  P4  (max, min) equal the extrema of the field and the oracle's
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sdf_tools_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def gpu_signed_d2(ctx, mask):
+    m = torch.from_numpy(np.ascontiguousarray(mask, dtype=np.uint8)).cuda()
+    out = torch.empty(mask.shape, dtype=torch.int32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.signed_d2_device(m.data_ptr(), *mask.shape, out.data_ptr())
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def check_full(ctx, mask, res):
+    want_s = O.signed_d2(mask)
+    got_s = gpu_signed_d2(ctx, mask)
+    assert np.array_equal(got_s, want_s), f"P1 failed: {(got_s != want_s).sum()} voxels differ"
+    want, wmx, wmn = O.build_sdf(mask, res)
+    got, (gmx, gmn) = ctx.build_from_mask(mask, res)
+    assert np.array_equal(np.signbit(got), mask != 0), "P0 failed"
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "P2 failed (not bit-identical to the oracle)"
+    assert (gmx, gmn) == (wmx, wmn), f"P4 failed: {(gmx, gmn)} vs {(wmx, wmn)}"
+    return got
+
+
+@pytest.mark.parametrize("shape,p,seed", [
+    ((64, 64, 64), 0.30, 1), ((33, 47, 29), 0.05, 2), ((1, 40, 20), 0.1, 3), ((40, 1, 20), 0.1, 4),
+    ((20, 40, 1), 0.1, 5), ((7, 5, 3), 0.5, 6), ((100, 100, 50), 0.01, 7), ((96, 128, 160), 0.002, 8),
+    ((130, 70, 257), 0.3, 9), ((2, 2, 2), 0.5, 10), ((1, 1, 1), 1.0, 11), ((300, 31, 65), 0.9, 12),
+])
+def test_random_grids(ctx, shape, p, seed):
+    mask = synth.iid(shape, p, seed)
+    check_full(ctx, mask, 0.1)
+
+
+def test_c1_config(ctx):
+    mask = synth.make_mask("c1")
+    got = check_full(ctx, mask, synth.CONFIGS["c1"]["res"])
+    if O.have_ref():   # dense iid grid: the reference's propagation is exact here -> literal 1e-5 target, whole grid
+        ref, rmx, rmn, _ = O.ref_build_sdf(mask, synth.CONFIGS["c1"]["res"])
+        assert np.allclose(got, ref, rtol=1e-5, atol=0)
+        assert np.array_equal(got, ref)
+
+
+def test_c2_sphere_256(ctx):
+    mask = synth.make_mask("c2")
+    check_full(ctx, mask, synth.CONFIGS["c2"]["res"])
+
+
+def test_sparse_vs_reference_p3(ctx):
+    mask = synth.make_mask("c2", (96, 96, 96))
+    got = check_full(ctx, mask, 0.05)
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    ref, _, _, _ = O.ref_build_sdf(mask, 0.05)
+    assert np.array_equal(np.signbit(ref), np.signbit(got))
+    differ = ref != got
+    assert (np.abs(ref[differ]) > np.abs(got[differ])).all(), "reference must only over-estimate"
+    assert 0 < differ.mean() < 0.03
+    agree = ~differ
+    assert np.allclose(got[agree], ref[agree], rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("fixture", ["fixture_single_cell", "fixture_demo_blocks", "fixture_tutorial_octant",
+                                     "fixture_walls_cross"])
+def test_reference_fixture_geometries(ctx, fixture):
+    mask, res = getattr(synth, fixture)()
+    check_full(ctx, mask, res)
+
+
+def test_degenerate_polarity(ctx):
+    for fill in (0, 1):
+        mask = np.full((9, 8, 7), fill, dtype=np.uint8)
+        sdf, (mx, mn) = ctx.build_from_mask(mask, 0.5)
+        want = np.inf if fill == 0 else -np.inf       # sdf_generation.hpp:104,254-256
+        assert np.all(sdf == want) and mx == want and mn == want
+    sdf, (mx, mn) = ctx.build_from_mask(np.zeros((0, 4, 4), np.uint8), 0.5)
+    assert sdf.size == 0 and mx == -np.inf and mn == np.inf     # :246-247 with no iterations
+
+
+def test_long_axes(ctx):
+    for shape in [(2048, 4, 8), (4, 2048, 8), (4, 8, 2048), (1500, 3, 33)]:
+        mask = synth.iid(shape, 0.003, 21)
+        check_full(ctx, mask, 0.01)
+
+
+def test_unsupported_axis(ctx):
+    from sdf_tools_b200 import SdfB200Error
+    with pytest.raises(SdfB200Error) as e:
+        ctx.build_from_mask(np.zeros((2049, 1, 1), np.uint8), 1.0)
+    assert e.value.code == -3
+
+
+def test_cells_entry_point(ctx):
+    from sdf_tools_b200.api import COLLISION_CELL_DTYPE
+    occ = synth.octree((64, 64, 64), 0.3, 5)
+    cells = np.zeros(occ.shape, dtype=COLLISION_CELL_DTYPE)
+    cells["occupancy"] = occ
+    cells["component"] = 7
+    for unknown in (False, True):
+        mask = O.pack_cells(cells, unknown)
+        want, wmx, wmn = O.build_sdf(mask, 0.02)
+        got, (mx, mn) = ctx.build_from_cells(cells, 0.02, unknown)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert (mx, mn) == (wmx, wmn)
+
+
+def test_point_cloud_256(ctx):
+    mask = synth.make_mask("c3", (256, 256, 256))
+    check_full(ctx, mask, 0.01)
