@@ -52,8 +52,10 @@ int sdf_b200_create(sdf_b200_ctx** out, int device);
 void sdf_b200_destroy(sdf_b200_ctx* ctx);
 const char* sdf_b200_last_error(const sdf_b200_ctx* ctx); /* ctx may be NULL: error of the last create() */
 
-/* Use an existing stream (e.g. torch's current stream) for all launches; NULL restores the context's own. */
-int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream);
+/* Stream for all launches and copies: use_own_stream != 0 selects the context's own non-blocking stream (the
+ * default after create); otherwise `cuda_stream` is used as given (e.g. torch's current stream; NULL = the CUDA
+ * default stream). */
+int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream, int use_own_stream);
 int sdf_b200_synchronize(sdf_b200_ctx* ctx);
 
 /* Pinned host buffers for the host-side entry points (optional; any host pointer works, pinned is faster). */
@@ -92,7 +94,7 @@ int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t 
                               int32_t* d_out);
 
 /* Device time of the last build on this context in milliseconds (CUDA events around the launch sequence);
- * per-kernel times in out_ms[0..3] = {pass 1 (x, binary), pass 2 (y), pass 3 (z + combine), total}. */
+ * per-kernel times in out_ms[0..3] = {pass 1 (z, binary), pass 2 (y), pass 3 (x + combine), total}. */
 int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4);
 /* Number of kernels the last build launched (for bench.py's gpu_launches). */
 int sdf_b200_last_launches(const sdf_b200_ctx* ctx);

@@ -20,7 +20,7 @@ SYMBOLS = [
     ("sdf_b200_create", _int, [C.POINTER(_vp), _int]),
     ("sdf_b200_destroy", None, [_vp]),
     ("sdf_b200_last_error", C.c_char_p, [_vp]),
-    ("sdf_b200_set_stream", _int, [_vp, _vp]),
+    ("sdf_b200_set_stream", _int, [_vp, _vp, _int]),
     ("sdf_b200_synchronize", _int, [_vp]),
     ("sdf_b200_host_alloc", _int, [C.POINTER(_vp), C.c_size_t]),
     ("sdf_b200_host_free", _int, [_vp]),

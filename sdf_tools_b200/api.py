@@ -87,7 +87,11 @@ class Context:
 
     # -------------------------------------------------------------------------------------- device buffers
     def set_stream(self, cuda_stream_ptr: int | None):
-        self._check(self._lib.sdf_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+        """Launch on the given CUDA stream handle (0 = the default stream); None = the context's own stream."""
+        if cuda_stream_ptr is None:
+            self._check(self._lib.sdf_b200_set_stream(self._h, C.c_void_p(0), 1))
+        else:
+            self._check(self._lib.sdf_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr), 0))
 
     def build_device(self, d_mask_ptr: int, nx: int, ny: int, nz: int, resolution: float, d_sdf_ptr: int):
         self._check(self._lib.sdf_b200_build_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz,
@@ -112,7 +116,7 @@ class Context:
     def last_timing(self):
         arr = (C.c_float * 4)()
         self._check(self._lib.sdf_b200_last_timing(self._h, arr))
-        return {"pass1_x_ms": arr[0], "pass2_y_ms": arr[1], "pass3_z_ms": arr[2], "total_ms": arr[3]}
+        return {"pass1_z_ms": arr[0], "pass2_y_ms": arr[1], "pass3_x_ms": arr[2], "total_ms": arr[3]}
 
     def last_launches(self) -> int:
         return int(self._lib.sdf_b200_last_launches(self._h))

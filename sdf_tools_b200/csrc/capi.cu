@@ -1,9 +1,8 @@
 // sdf_tools_b200/csrc/capi.cu -- the C ABI of libsdf_b200.so (include/sdf_b200.h) over the kernel launchers.
 // Host orchestration of sdf_generation::ExtractSignedDistanceField<T> (sdf_generation.hpp:209-271):
-//   mask -> K1 (x, binary) -> K2 (y) -> K3 (z + combine) -> f32 field + (max, min).
+//   mask -> K1 (z, binary) -> K2 (y) -> K3 (x + combine) -> f32 field + (max, min).
 #include "../../include/sdf_b200.h"
 #include "edt_kernels.cuh"
-#include "line_hull.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -112,10 +111,10 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
 
 const char* sdf_b200_last_error(const sdf_b200_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 
-int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream)
+int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream, int use_own_stream)
 {
     if (!ctx) return SDF_B200_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = use_own_stream ? ctx->own_stream : (cudaStream_t)cuda_stream;   // NULL = CUDA default stream
     return SDF_B200_OK;
 }
 
@@ -153,15 +152,17 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
     CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
     if (nx * ny * nz == 0) { ctx->built = true; ctx->res = res; return SDF_B200_OK; }
     CK(cudaEventRecord(ctx->ev[0], st), "event");
-    CK(sdfb200::launch_binary_x(d_mask, d_field, (int)nx, ny * nz, st), "launch binary_x");
+    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, st), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
-        CK(sdfb200::launch_hull_strided(d_field, (int)ny, nz, nz, nx, ny * nz, st), "launch hull_strided");
+        CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, st),
+           "launch band_strided(y)");
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st), "event");
-    CK(sdfb200::launch_hull_contig(d_field, (int)nz, nx * ny, final_pass, res, ctx->d_ext, st), "launch hull_contig");
+    CK(sdfb200::launch_band_strided(d_field, (int)nx, ny * nz, ny * nz, 1, 0, final_pass, res, ctx->d_ext, st),
+       "launch band_strided(x)");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[3], st), "event");
     ctx->timed = true;
