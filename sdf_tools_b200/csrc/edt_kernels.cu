@@ -160,13 +160,12 @@ __global__ void __launch_bounds__(32 * LPC) band_strided_kernel(int32_t* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BandTile T;
     {
-        unsigned char* p = smem_raw;
-        T.S = reinterpret_cast<uint32_t*>(p);      p += (size_t)nb * B * LPC * 4;
-        T.meta = reinterpret_cast<uint32_t*>(p);   p += (size_t)nb * LPC * 4;
-        T.pcA[0] = reinterpret_cast<int16_t*>(p);  p += (size_t)nb * LPC * 2;
-        T.pcA[1] = reinterpret_cast<int16_t*>(p);  p += (size_t)nb * LPC * 2;
-        T.pcE[0] = reinterpret_cast<int16_t*>(p);  p += (size_t)nb * LPC * 2;
-        T.pcE[1] = reinterpret_cast<int16_t*>(p);
+        uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw);
+        T.S = p;      p += (uint32_t)nb * B * LPC * 4;
+        T.meta = p;   p += (uint32_t)nb * LPC * 4;
+        T.pcA = p;    p += (uint32_t)nb * LPC * 4;
+        T.pcE = p;
+        T.pcstride = nb * LPC;
     }
     const int c = threadIdx.x % LPC, b = threadIdx.x / LPC;
     const int64_t col = (int64_t)blockIdx.x * LPC + c;

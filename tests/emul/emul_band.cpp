@@ -20,8 +20,8 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
     const int nb = (n + B - 1) / B;
     int nlevels = 0; while ((1 << nlevels) < nb) ++nlevels;
     std::vector<uint32_t> S((size_t)nb * B * LPC), meta((size_t)nb * LPC);
-    std::vector<int16_t> a0((size_t)nb * LPC), a1((size_t)nb * LPC), e0((size_t)nb * LPC), e1((size_t)nb * LPC);
-    BandTile T; T.S = S.data(); T.meta = meta.data(); T.pcA[0] = a0.data(); T.pcA[1] = a1.data(); T.pcE[0] = e0.data(); T.pcE[1] = e1.data();
+    std::vector<int16_t> a01((size_t)2 * nb * LPC), e01((size_t)2 * nb * LPC);
+    BandTile T; T.S = (bh_addr_t)S.data(); T.meta = (bh_addr_t)meta.data(); T.pcA = (bh_addr_t)a01.data(); T.pcE = (bh_addr_t)e01.data(); T.pcstride = nb * LPC;
     std::vector<typename BH::pcw_t> Pw((size_t)nb * LPC), PCw((size_t)nb * LPC);
     std::vector<int> order((size_t)nb * LPC);
     for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
@@ -34,7 +34,7 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
             int32_t in[B];
             bool prevpol = false;
             if (c0 + c < ncols) {
-                for (int i = 0; i < B; i++) { const int q = b * B + i; in[i] = q < n ? g[(int64_t)q * line_stride + c0 + c] : 0; }
+                for (int i = 0; i < B; i++) { const int q = b * B + i; in[i] = q < n ? g[(int64_t)q * line_stride + c0 + c] : SDF_INF; }
                 const int qp = b > 0 ? b * B - 1 : 0;
                 prevpol = (qp < n) ? g[(int64_t)qp * line_stride + c0 + c] < 0 : false;
             } else { for (int i = 0; i < B; i++) in[i] = SDF_INF; }
