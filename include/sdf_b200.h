@@ -99,6 +99,11 @@ int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4);
 /* Number of kernels the last build launched (for bench.py's gpu_launches). */
 int sdf_b200_last_launches(const sdf_b200_ctx* ctx);
 
+/* Diagnostics: when enabled, thread 0 of the first 1024 CTAs of each envelope pass stores clock64() at its phase
+ * boundaries (start, loaded, built, barrier, merged, queried) into a device buffer; `out` (2*1024*8 values, pass 2
+ * then pass 3) receives them.  enable = 0 frees the buffer.  Not for production use. */
+int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ SYMBOLS = [
     ("sdf_b200_signed_d2_device", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),
     ("sdf_b200_last_launches", _int, [_vp]),
+    ("sdf_b200_debug_phase_clocks", _int, [_vp, _int, C.POINTER(C.c_longlong), _int]),
 ]
 
 _lib = None

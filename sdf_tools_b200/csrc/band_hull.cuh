@@ -98,6 +98,12 @@ SDF_HD bool bh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t
     return lhs >= rhs;
 }
 
+#if defined(BH_COUNT) && !defined(__CUDA_ARCH__)
+#define BH_TICK(x) (++bh_counters[x])
+static long long bh_counters[8];
+#else
+#define BH_TICK(x) ((void)0)
+#endif
 constexpr int BH_NONE = -1;
 constexpr int BH_BIG = 0x7fff;          // "no run boundary after": larger than any position
 
@@ -148,120 +154,90 @@ struct BandHull {
 
     static SDF_HD int sidx(int b, int k, int c) { return ((b << LOGB) + k) * LPC + c; }
     static SDF_HD int midx(int b, int c) { return b * LPC + c; }
-    static SDF_HD uint32_t ldS(const BandTile& T, int b, int k, int c) { return bh_ld32(T.S + 4u * (uint32_t)sidx(b, k, c)); }
+    // A hull vertex is addressed by its SLOT u = b*B + k (band b, index k in that band's stack).
+    static SDF_HD uint32_t ldU(const BandTile& T, int u, int c) { return bh_ld32(T.S + 4u * (uint32_t)(u * LPC + c)); }
+    static SDF_HD uint32_t ldS(const BandTile& T, int b, int k, int c) { return ldU(T, (b << LOGB) + k, c); }
     static SDF_HD uint32_t ldM(const BandTile& T, int b, int c) { return bh_ld32(T.meta + 4u * (uint32_t)midx(b, c)); }
     static SDF_HD void stM(const BandTile& T, int b, int c, uint32_t v) { bh_st32(T.meta + 4u * (uint32_t)midx(b, c), v); }
+    static SDF_HD int u_pos(int u, uint32_t e) { return (u & ~(B - 1)) + e_rel(e); }
 
-    // A hull vertex reference: band, index inside the band stack, and its decoded position / height.
-    struct Ref { int b, k, pos; int32_t h; };
-
-    static SDF_HD Ref load_ref(const BandTile& T, int c, int b, int k) {
-        const uint32_t e = ldS(T, b, k, c);
-        Ref r; r.b = b; r.k = k; r.pos = (b << LOGB) + e_rel(e); r.h = e_h(e);
-        return r;
-    }
-
-    // Predecessor of (b,k) inside the same run, not below band glo.  Returns false if there is none.
-    static SDF_HD bool prev_entry(const BandTile& T, int c, int glo, const Ref& x, Ref& out) {
-        const uint32_t e = ldS(T, x.b, x.k, c);
-        if (e_rs(e)) return false;                       // x is the first vertex of its run
-        const uint32_t m = ldM(T, x.b, c);
-        if (x.k > m_lo(m)) { out = load_ref(T, c, x.b, x.k - 1); return true; }
-        for (int b2 = x.b - 1; b2 >= glo; --b2) {
-            const uint32_t m2 = ldM(T, b2, c);
-            if (m_tail(m2)) return false;
-            if (m_hi(m2) > m_lo(m2)) { out = load_ref(T, c, b2, m_hi(m2) - 1); return true; }
-            if (m_any(m2)) return false;
-        }
-        return false;
-    }
-
-    // Successor of (b,k) inside the same run, below band ghi.
-    static SDF_HD bool next_entry(const BandTile& T, int c, int ghi, const Ref& x, Ref& out) {
-        const uint32_t m = ldM(T, x.b, c);
-        if (x.k + 1 < m_hi(m)) {
-            const uint32_t e = ldS(T, x.b, x.k + 1, c);
-            if (e_rs(e)) return false;
-            out.b = x.b; out.k = x.k + 1; out.pos = (x.b << LOGB) + e_rel(e); out.h = e_h(e);
-            return true;
-        }
-        if (m_tail(m)) return false;
-        return first_from(T, c, x.b + 1, ghi, out);
-    }
-
-    // First vertex of the run that enters band b0 from the left (no polarity change up to it), bands [b0, ghi).
-    static SDF_HD bool first_from(const BandTile& T, int c, int b0, int ghi, Ref& out) {
+    // First vertex of the run that enters band b0 from the left (no polarity change up to it), bands [b0, ghi):
+    // returns its slot (and the packed entry / the meta word of its band) or -1.
+    static SDF_HD int first_from(const BandTile& T, int c, int b0, int ghi, uint32_t& e, uint32_t& m) {
         for (int b2 = b0; b2 < ghi; ++b2) {
-            const uint32_t m2 = ldM(T, b2, c);
-            if (m_hi(m2) > m_lo(m2)) {
-                const uint32_t e = ldS(T, b2, m_lo(m2), c);
-                if (e_rs(e)) return false;
-                out.b = b2; out.k = m_lo(m2); out.pos = (b2 << LOGB) + e_rel(e); out.h = e_h(e);
-                return true;
+            m = ldM(T, b2, c);
+            if (m_hi(m) > m_lo(m)) {
+                const int u = (b2 << LOGB) + m_lo(m);
+                e = ldU(T, u, c);
+                return e_rs(e) ? -1 : u;
             }
-            if (m_any(m2)) return false;
+            if (m_any(m)) return -1;
         }
-        return false;
+        return -1;
     }
-
     // Last vertex of the run that leaves band b0 to the right (no polarity change after it), bands [glo, b0].
-    static SDF_HD bool last_upto(const BandTile& T, int c, int b0, int glo, Ref& out) {
+    static SDF_HD int last_upto(const BandTile& T, int c, int b0, int glo, uint32_t& e, uint32_t& m) {
         for (int b2 = b0; b2 >= glo; --b2) {
-            const uint32_t m2 = ldM(T, b2, c);
-            if (m_tail(m2)) return false;
-            if (m_hi(m2) > m_lo(m2)) { out = load_ref(T, c, b2, m_hi(m2) - 1); return true; }
-            if (m_any(m2)) return false;
+            m = ldM(T, b2, c);
+            if (m_tail(m)) return -1;
+            if (m_hi(m) > m_lo(m)) {
+                const int u = (b2 << LOGB) + m_hi(m) - 1;
+                e = ldU(T, u, c);
+                return u;
+            }
+            if (m_any(m)) return -1;
         }
-        return false;
+        return -1;
+    }
+    // Predecessor of vertex u (entry eu, band meta mu) inside the same run, not below band glo; -1 if none.
+    static SDF_HD int prev_of(const BandTile& T, int c, int glo, int u, uint32_t eu, uint32_t mu, uint32_t& e, uint32_t& m) {
+        if (e_rs(eu)) return -1;                              // u is the first vertex of its run
+        if ((u & (B - 1)) > m_lo(mu)) { m = mu; e = ldU(T, u - 1, c); return u - 1; }
+        return last_upto(T, c, (u >> LOGB) - 1, glo, e, m);
+    }
+    // Successor of vertex u (band meta mu) inside the same run, below band ghi; -1 if none.
+    static SDF_HD int next_of(const BandTile& T, int c, int ghi, int u, uint32_t mu, uint32_t& e, uint32_t& m) {
+        if ((u & (B - 1)) + 1 < m_hi(mu)) {
+            m = mu; e = ldU(T, u + 1, c);
+            return e_rs(e) ? -1 : u + 1;
+        }
+        if (m_tail(mu)) return -1;
+        return first_from(T, c, (u >> LOGB) + 1, ghi, e, m);
     }
 
     // ------------------------------------------------------------------------------------------- phase build
-    // in[i] = signed value at position b*B + i (SDF_INF for positions >= n); prevpol = polarity of position
-    // b*B - 1 (for b == 0: polarity of position 0).  Outputs the band's polarity / run-start bit words.
     static SDF_HD int pcw_lo(pcw_t m) { return (LOGB > 5) ? bh_lobit64((uint64_t)m) : bh_lobit((uint32_t)m); }
     static SDF_HD int pcw_hi(pcw_t m) { return (LOGB > 5) ? bh_hibit64((uint64_t)m) : bh_hibit((uint32_t)m); }
     static SDF_HD pcw_t low_incl(int i) { return (((pcw_t)2) << i) - 1; }          // bits [0, i]  (i = width-1 -> all ones)
 
-    static SDF_HD void build(const BandTile& T, int c, int b, int n, const int32_t* in, bool prevpol,
-                             pcw_t& Pw, pcw_t& PCw) {
+    // The band's raw signed values must already sit in its own stack slots (slot i = position b*B + i, SDF_INF for
+    // positions >= n): the hull is built IN PLACE -- vertex k <= i overwrites slot k after slot i has been read.
+    // prevpol = polarity of position b*B - 1 (for b == 0: polarity of position 0).
+    static SDF_HD void build(const BandTile& T, int c, int b, int n, bool prevpol, pcw_t& Pw, pcw_t& PCw) {
         const int base = b << LOGB;
-        // polarity word: one funnel shift per element, bit-reversed at the end
-        pcw_t pw;
-        {
-            uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-            for (int i = 0; i < B; ++i) {
-                if (i < 32) w0 = bh_shift_in_sign(w0, in[i]); else w1 = bh_shift_in_sign(w1, in[i]);
-            }
-            w0 = bh_brev(w0);
-            if (B < 32) w0 >>= (32 - (B < 32 ? B : 0)) & 31;
-            if constexpr (LOGB > 5) { w1 = bh_brev(w1); pw = (pcw_t)w0 | ((pcw_t)w1 << 32); } else { pw = w0; (void)w1; }
-        }
         int nvalid = n - base;
         nvalid = nvalid < 0 ? 0 : (nvalid > B ? B : nvalid);
-        const pcw_t lim = nvalid ? low_incl(nvalid - 1) : (pcw_t)0;
-        pw &= lim;
-        const pcw_t pcw = (pw ^ ((pw << 1) | (pcw_t)prevpol)) & lim;
-        const bool anypc = pcw != 0;
-
-        const bh_addr_t st = T.S + 4u * (uint32_t)sidx(b, 0, c);   // this thread's stack: slot k at st + k*LPC*4
-        int k = 0, cnt = 0;                           // entries in the band / in the current run
+        const bh_addr_t st = T.S + 4u * (uint32_t)sidx(b, 0, c);   // this thread's slots: slot k at st + k*LPC*4
+        pcw_t pw = 0, pcw = 0;
+        int k = 0, cnt = 0;                           // vertices in the band / in the current run
         int tp = 0, sp = 0, dPts = 1;
         int32_t tY = 0, sY = 0, dYts = 0;
-        pcw_t notbelow = ~(pcw_t)0;                   // positions after the previous vertex of this band
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const int32_t v = in[i];
-            const int32_t h = v < 0 ? -v : v;
+        bool pcflag = false;                          // a run boundary since the previous vertex of this band
+#pragma unroll 2
+        for (int i = 0; i < nvalid; ++i) {
+            const int32_t v = (int32_t)bh_ld32(st + (uint32_t)(i * (LPC * 4)));
+            const bool pol = v < 0;
+            const int32_t h = pol ? -v : v;
+            if (pol != prevpol) { pcw |= (pcw_t)1 << i; pcflag = true; prevpol = pol; }
+            if (pol) pw |= (pcw_t)1 << i;
             if (h < SDF_INF) {
-                const bool pcf = (pcw & notbelow & low_incl(i)) != 0;     // a run boundary since the previous vertex
-                if (pcf) cnt = 0;
+                if (pcflag) cnt = 0;
                 const int q = base + i;
                 const int32_t Y = q * q + h;
                 int32_t A = Y - tY;
                 int Bq = q - tp;
                 while (cnt >= 2 && (long long)dYts * (long long)Bq >= (long long)A * (long long)dPts) {
-                    --k; --cnt;
+                    --k; --cnt; BH_TICK(0);
                     tp = sp; tY = sY;
                     if (cnt >= 2) {
                         const uint32_t e = bh_ld32(st + (uint32_t)((k - 2) * (LPC * 4)));
@@ -271,15 +247,15 @@ struct BandHull {
                     dYts = tY - sY; dPts = tp - sp;
                     A = Y - tY; Bq = q - tp;
                 }
-                bh_st32(st + (uint32_t)(k * (LPC * 4)), (uint32_t)h | ((uint32_t)i << 24) | ((uint32_t)pcf << 30));
+                bh_st32(st + (uint32_t)(k * (LPC * 4)), (uint32_t)h | ((uint32_t)i << 24) | ((uint32_t)pcflag << 30));
                 ++k; ++cnt;
                 sp = tp; sY = tY; tp = q; tY = Y;
                 dYts = A; dPts = Bq;
-                notbelow = ~low_incl(i);
+                pcflag = false;
             }
         }
-        const bool tailpc = (pcw & notbelow) != 0;
-        stM(T, b, c, mk_meta(0, k, tailpc, anypc, (pcw & 1) != 0));
+        const bool anypc = pcw != 0;
+        stM(T, b, c, mk_meta(0, k, pcflag, anypc, (pcw & 1) != 0));
         bh_st16(T.pcA + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_hi(pcw) : -1);
         bh_st16(T.pcE + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_lo(pcw) : BH_BIG);
         Pw = pw; PCw = pcw;
@@ -304,52 +280,83 @@ struct BandHull {
         // (a) seam
         const int g = 1 << lv;
         if ((b & (2 * g - 1)) != g) return;
-        if (m_head(ldM(T, b, c))) return;            // a run starts exactly at the seam
+        const uint32_t mR = ldM(T, b, c);
+        if (m_head(mR)) return;                        // a run starts exactly at the seam
+        {   // fast path: the two bands next to the seam hold the bridge end points and nothing has to be dropped
+            const uint32_t mL = ldM(T, b - 1, c);
+            const int loR = m_lo(mR), hiR = m_hi(mR), loL = m_lo(mL), hiL = m_hi(mL);
+            if (hiL > loL && !m_tail(mL) && hiR > loR) {
+                const uint32_t eL = ldS(T, b - 1, hiL - 1, c), eR = ldS(T, b, loR, c);
+                const uint32_t eL2 = ldS(T, b - 1, hiL >= 2 ? hiL - 2 : 0, c);
+                const uint32_t eR2 = ldS(T, b, loR + 1 < B ? loR + 1 : loR, c);
+                if (e_rs(eR)) return;                  // the run ends before the first vertex right of the seam
+                const bool simpleL2 = (hiL - 2 >= loL) && !e_rs(eL);
+                const bool noL2 = e_rs(eL);
+                const bool simpleR2 = loR + 1 < hiR;
+                if ((simpleL2 || noL2) && (simpleR2 || m_tail(mR))) {
+                    const int Lp = ((b - 1) << LOGB) + e_rel(eL), Rp = (b << LOGB) + e_rel(eR);
+                    const int32_t LYf = Lp * Lp + e_h(eL), RYf = Rp * Rp + e_h(eR);
+                    bool dom = false;
+                    if (simpleL2) {
+                        const int L2p = ((b - 1) << LOGB) + e_rel(eL2);
+                        dom = bh_dominated(L2p, L2p * L2p + e_h(eL2), Lp, LYf, Rp, RYf);
+                    }
+                    if (simpleR2 && !e_rs(eR2)) {
+                        const int R2p = (b << LOGB) + e_rel(eR2);
+                        dom = dom || bh_dominated(Lp, LYf, Rp, RYf, R2p, R2p * R2p + e_h(eR2));
+                    }
+                    if (!dom) return;
+                }
+            }
+        }
         const int glo = b - g;
         int ghi = b + g; if (ghi > nb) ghi = nb;
-        Ref L, R, L2, R2;
-        if (!last_upto(T, c, b - 1, glo, L)) return;
-        if (!first_from(T, c, b, ghi, R)) return;
-        bool hasL2 = prev_entry(T, c, glo, L, L2);
-        bool hasR2 = next_entry(T, c, ghi, R, R2);
-        int32_t LY = L.pos * L.pos + L.h, RY = R.pos * R.pos + R.h;
+        // general path: two cursors walk the common tangent.  L / R = current bridge ends (slot, entry, band meta),
+        // L2 / R2 = their neighbours further inside.  Bands are trimmed in registers and written back when left.
+        uint32_t eL, mLm, eR, mRm, eL2 = 0, mL2 = 0, eR2 = 0, mR2 = 0;
+        int uL = last_upto(T, c, b - 1, glo, eL, mLm);
+        if (uL < 0) return;
+        int uR = first_from(T, c, b, ghi, eR, mRm);
+        if (uR < 0) return;
+        int uL2 = prev_of(T, c, glo, uL, eL, mLm, eL2, mL2);
+        int uR2 = next_of(T, c, ghi, uR, mRm, eR2, mR2);
+        int Lp = u_pos(uL, eL), Rp = u_pos(uR, eR);
+        int32_t LY = Lp * Lp + e_h(eL), RY = Rp * Rp + e_h(eR);
+        bool dirtyL = false, dirtyR = false;
         for (;;) {
             bool changed = false;
-            while (hasL2 && bh_dominated(L2.pos, L2.pos * L2.pos + L2.h, L.pos, LY, R.pos, RY)) {
-                stM(T, L.b, c, ldM(T, L.b, c) - (1u << 8));  // drop L: trim its band from the back
-                // bands between L2 and L that became empty stay empty; L2 becomes the tail
-                L = L2; LY = L.pos * L.pos + L.h;
-                hasL2 = prev_entry(T, c, glo, L, L2);
-                changed = true;
+            while (uL2 >= 0) {
+                const int L2p = u_pos(uL2, eL2);
+                const int32_t L2Y = L2p * L2p + e_h(eL2);
+                if (!bh_dominated(L2p, L2Y, Lp, LY, Rp, RY)) break;
+                BH_TICK(1 + (lv < 5 ? lv : 5));
+                if ((uL2 >> LOGB) != (uL >> LOGB))             // leaving a band: it is now empty
+                    stM(T, uL >> LOGB, c, (mLm & ~(127u << 8)) | ((uint32_t)m_lo(mLm) << 8));
+                uL = uL2; eL = eL2; mLm = mL2; Lp = L2p; LY = L2Y;
+                dirtyL = true; changed = true;
+                uL2 = prev_of(T, c, glo, uL, eL, mLm, eL2, mL2);
             }
-            while (hasR2 && bh_dominated(L.pos, LY, R.pos, RY, R2.pos, R2.pos * R2.pos + R2.h)) {
-                stM(T, R.b, c, ldM(T, R.b, c) + 1u);         // drop R: trim its band from the front
-                R = R2; RY = R.pos * R.pos + R.h;
-                hasR2 = next_entry(T, c, ghi, R, R2);
-                changed = true;
+            while (uR2 >= 0) {
+                const int R2p = u_pos(uR2, eR2);
+                const int32_t R2Y = R2p * R2p + e_h(eR2);
+                if (!bh_dominated(Lp, LY, Rp, RY, R2p, R2Y)) break;
+                BH_TICK(1 + (lv < 5 ? lv : 5));
+                if ((uR2 >> LOGB) != (uR >> LOGB))
+                    stM(T, uR >> LOGB, c, (mRm & ~127u) | (uint32_t)m_hi(mRm));
+                uR = uR2; eR = eR2; mRm = mR2; Rp = R2p; RY = R2Y;
+                dirtyR = true; changed = true;
+                uR2 = next_of(T, c, ghi, uR, mRm, eR2, mR2);
             }
             if (!changed) break;
         }
+        if (dirtyL) stM(T, uL >> LOGB, c, (mLm & ~(127u << 8)) | ((uint32_t)((uL & (B - 1)) + 1) << 8));
+        if (dirtyR) stM(T, uR >> LOGB, c, (mRm & ~127u) | (uint32_t)(uR & (B - 1)));
     }
 
     // ------------------------------------------------------------------------------------------- phase query
     // Emits out(p) for p in the band through `emit(i, value)`, i = position inside the band, in increasing i.
     static constexpr int32_t NOSITE = 0x60000000;       // height of a non-existent "next" vertex: never wins
     static constexpr int FAR = 40000;                    // distance to a non-existent zero site: FAR^2 > SDF_INF
-
-    // successor of vertex (cb, ck) of the same run -> (nb_, nk, npos, nh); nh = NOSITE if there is none
-    static SDF_HD void load_next(const BandTile& T, int c, int nbands, int cb, int ck, int& nb_, int& nk, int& npos, int32_t& nh) {
-        const uint32_t m = ldM(T, cb, c);
-        if (ck + 1 < m_hi(m)) {
-            const uint32_t e = ldS(T, cb, ck + 1, c);
-            nb_ = cb; nk = ck + 1; npos = (cb << LOGB) + e_rel(e);
-            nh = e_rs(e) ? NOSITE : e_h(e);
-            return;
-        }
-        Ref r;
-        if (!m_tail(m) && first_from(T, c, cb + 1, nbands, r)) { nb_ = r.b; nk = r.k; npos = r.pos; nh = r.h; }
-        else { nb_ = cb; nk = ck; npos = 0; nh = NOSITE; }
-    }
 
     template <typename Emit>
     static SDF_HD void query(const BandTile& T, int c, int b, int nb, int n, int nlevels, pcw_t Pw, pcw_t PCw, Emit emit) {
@@ -361,10 +368,12 @@ struct BandHull {
         const int a0 = (b > 0) ? bh_ld16(T.pcA + 2u * (uint32_t)(fin * T.pcstride + midx(b - 1, c))) : -1;         // last run start before the band
         const int e_after = (b + 1 < nb) ? bh_ld16(T.pcE + 2u * (uint32_t)(fin * T.pcstride + midx(b + 1, c))) : BH_BIG;   // first run start after it
         const uint32_t mym = ldM(T, b, c);
-        const int myhi = m_hi(mym);
-        int ks = m_lo(mym);                                 // scan pointer over this band's own vertices
-        // current / next hull vertex as scalars; "none" is encoded in the heights
-        int cb = b, ck = 0, cpos = base, nb_ = b, nk = 0, npos = 0;
+        const int myhi = base + m_hi(mym);
+        int us = base + m_lo(mym);                          // scan slot over this band's own vertices
+        // current / next hull vertex as scalars; "none" is encoded in the heights.
+        // cu = slot of cur, cm = meta of its band; nu/ne/nm = slot, entry, band meta of next.
+        int cu = base, cpos = base, nu = -1, npos = 0;
+        uint32_t cm = mym, nm = mym;
         int32_t ch = SDF_INF, nh = NOSITE;
         int e;
         {
@@ -374,59 +383,74 @@ struct BandHull {
         int dl = (a0 >= 1) ? base - a0 + 1 : FAR;           // p - a + 1: distance to the zero site before the run
         int dr = (e < n) ? e - base : FAR;                  // e - p:     distance to the zero site after the run
         if (!(PCw & 1)) {                                   // position `base` continues a run from the left
-            Ref Lr, Rr;
-            const bool hasL = (b > 0) && last_upto(T, c, b - 1, 0, Lr);
-            const bool hasR = first_from(T, c, b, nb, Rr);
-            bool have = false;
-            Ref cur;
-            if (hasR && (!hasL || (base - Rr.pos) * (base - Rr.pos) + Rr.h <= (base - Lr.pos) * (base - Lr.pos) + Lr.h)) {
-                cur = Rr; have = true;
-            } else if (hasL) {
-                cur = Lr; have = true;
+            uint32_t eLq = 0, mLq = 0, eRq = 0, mRq = 0;
+            const int uLq = (b > 0) ? last_upto(T, c, b - 1, 0, eLq, mLq) : -1;
+            const int uRq = first_from(T, c, b, nb, eRq, mRq);
+            int u = -1; uint32_t eu = 0, mu = 0;
+            if (uRq >= 0) {
+                const int rp = u_pos(uRq, eRq);
+                bool takeR = uLq < 0;
+                if (!takeR) { const int lp = u_pos(uLq, eLq); takeR = (base - rp) * (base - rp) + e_h(eRq) <= (base - lp) * (base - lp) + e_h(eLq); }
+                if (takeR) { u = uRq; eu = eRq; mu = mRq; }
+            }
+            if (u < 0 && uLq >= 0) {
+                u = uLq; eu = eLq; mu = mLq;
                 for (;;) {                                  // local search towards the minimiser of `base`
-                    Ref pr;
-                    if (!prev_entry(T, c, 0, cur, pr)) break;
-                    const int dc = base - cur.pos, dp = base - pr.pos;
-                    if (dp * dp + pr.h < dc * dc + cur.h) cur = pr; else break;
+                    uint32_t ep = 0, mp = 0;
+                    const int up = prev_of(T, c, 0, u, eu, mu, ep, mp);
+                    if (up < 0) break;
+                    const int dc = base - u_pos(u, eu), dp = base - u_pos(up, ep);
+                    if (dp * dp + e_h(ep) < dc * dc + e_h(eu)) { u = up; eu = ep; mu = mp; } else break;
                 }
             }
-            if (have) {
-                cb = cur.b; ck = cur.k; cpos = cur.pos; ch = cur.h;
-                load_next(T, c, nb, cb, ck, nb_, nk, npos, nh);
+            if (u >= 0) {
+                cu = u; cm = mu; cpos = u_pos(u, eu); ch = e_h(eu);
+                uint32_t en = 0;
+                nu = next_of(T, c, nb, cu, cm, en, nm);
+                if (nu >= 0) { npos = u_pos(nu, en); nh = e_h(en); }
             }
         }
-#pragma unroll 8
-        for (int i = 0; i < B; ++i) {
-            if (i >= nvalid) break;
+#pragma unroll 2
+        for (int i = 0; i < nvalid; ++i) {
             const int p = base + i;
             if ((PCw >> i) & 1) {                           // a new run starts at p
                 const pcw_t rest = (i + 1 < B) ? (PCw >> (i + 1)) : (pcw_t)0;
                 e = rest ? p + 1 + pcw_lo(rest) : e_after;
                 dl = 1;
                 dr = (e < n) ? e - p : FAR;
-                ch = SDF_INF; nh = NOSITE; cpos = p;
-                bool have = false;
-                Ref r;
-                while (ks < myhi && e_rel(ldS(T, b, ks, c)) < i) ++ks;      // vertices of earlier runs
-                if (ks < myhi) {
-                    r = load_ref(T, c, b, ks);
-                    have = r.pos < e;
-                } else if (!rest && e_after > ((b + 1) << LOGB)) {
+                ch = SDF_INF; nh = NOSITE; cpos = p; nu = -1;
+                int u = -1; uint32_t eu = 0, mu = mym;
+                while (us < myhi && e_rel(ldU(T, us, c)) < i) ++us;            // vertices of earlier runs
+                if (us < myhi) {
+                    eu = ldU(T, us, c);
+                    if (u_pos(us, eu) < e) u = us;
+                } else if (!rest && e_after > ((b + 1) << LOGB) && b + 1 < nb) {
                     // the run continues into later bands and has no vertex here: its first vertex there
-                    have = (b + 1 < nb) && first_from(T, c, b + 1, nb, r);
+                    u = first_from(T, c, b + 1, nb, eu, mu);
                 }
-                if (have) {
-                    cb = r.b; ck = r.k; cpos = r.pos; ch = r.h;
-                    load_next(T, c, nb, cb, ck, nb_, nk, npos, nh);
+                if (u >= 0) {
+                    cu = u; cm = mu; cpos = u_pos(u, eu); ch = e_h(eu);
+                    uint32_t en = 0;
+                    nu = next_of(T, c, nb, cu, cm, en, nm);
+                    if (nu >= 0) { npos = u_pos(nu, en); nh = e_h(en); }
                 }
             }
             int dc = p - cpos, dn = p - npos;
             int32_t vc = dc * dc + ch;
             int32_t vn = dn * dn + nh;
             while (vn <= vc) {                              // the next vertex takes over
-                cb = nb_; ck = nk; cpos = npos; ch = nh;
+                cu = nu; cm = nm; cpos = npos; ch = nh;
                 vc = vn;
-                load_next(T, c, nb, cb, ck, nb_, nk, npos, nh);
+                nh = NOSITE;
+                if ((cu & (B - 1)) + 1 < m_hi(cm)) {        // fast path: the following slot of the same band
+                    const uint32_t en = ldU(T, cu + 1, c);
+                    nu = cu + 1; npos = u_pos(nu, en);
+                    if (!e_rs(en)) nh = e_h(en);
+                } else {
+                    uint32_t en = 0;
+                    nu = next_of(T, c, nb, cu, cm, en, nm);
+                    if (nu >= 0) { npos = u_pos(nu, en); nh = e_h(en); }
+                }
                 dn = p - npos;
                 vn = dn * dn + nh;
             }

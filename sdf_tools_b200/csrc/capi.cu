@@ -15,6 +15,9 @@ struct sdf_b200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int* d_ext = nullptr;              // [0] max +d2 over free voxels, [1] max d2 over filled voxels
+    float* d_lut = nullptr;            // (float)(sqrt((double)m)*res) for m < LUT_N at resolution lut_res
+    double lut_res = -1.0;
+    long long* d_dbg = nullptr;        // optional phase clocks of the band kernels: [pass 2|3][1024 CTAs][8]
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
     int launches = 0;
@@ -102,6 +105,8 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->d_ext) cudaFree(ctx->d_ext);
+    if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     if (ctx->d_out) cudaFree(ctx->d_out);
@@ -151,17 +156,25 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
     ctx->timed = false;
     CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
     if (nx * ny * nz == 0) { ctx->built = true; ctx->res = res; return SDF_B200_OK; }
+    constexpr int LUT_N = 1 << 20;                 // 4 MB: stays resident in the 126 MB L2
+    if (final_pass && (ctx->d_lut == nullptr || ctx->lut_res != res)) {
+        if (!ctx->d_lut) CK(cudaMalloc(&ctx->d_lut, (size_t)LUT_N * sizeof(float)), "cudaMalloc(lut)");
+        CK(sdfb200::launch_sqrt_lut(ctx->d_lut, LUT_N, res, st), "launch sqrt_lut");
+        ctx->lut_res = res;
+        ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->ev[0], st), "event");
     CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, st), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
-        CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, st),
+        CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, ctx->d_dbg, nullptr, 0, st),
            "launch band_strided(y)");
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st), "event");
-    CK(sdfb200::launch_band_strided(d_field, (int)nx, ny * nz, ny * nz, 1, 0, final_pass, res, ctx->d_ext, st),
+    CK(sdfb200::launch_band_strided(d_field, (int)nx, ny * nz, ny * nz, 1, 0, final_pass, res, ctx->d_ext, ctx->d_dbg ? ctx->d_dbg + 1024 * 8 : nullptr,
+                                    final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
        "launch band_strided(x)");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[3], st), "event");
@@ -277,5 +290,23 @@ int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4)
 }
 
 int sdf_b200_last_launches(const sdf_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, int n)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t bytes = (size_t)2 * 1024 * 8 * sizeof(long long);
+    if (enable && !ctx->d_dbg) {
+        CK(cudaMalloc(&ctx->d_dbg, bytes), "cudaMalloc(debug clocks)");
+        CK(cudaMemset(ctx->d_dbg, 0, bytes), "memset");
+    }
+    if (out && n > 0 && ctx->d_dbg) {
+        CK(cudaStreamSynchronize(ctx->stream), "sync");
+        const size_t want = (size_t)n * sizeof(long long);
+        CK(cudaMemcpy(out, ctx->d_dbg, want < bytes ? want : bytes, cudaMemcpyDeviceToHost), "copy debug clocks");
+    }
+    if (!enable && ctx->d_dbg) { cudaFree(ctx->d_dbg); ctx->d_dbg = nullptr; }
+    return SDF_B200_OK;
+}
 
 }  // extern "C"

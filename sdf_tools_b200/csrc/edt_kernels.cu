@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace sdfb200 {
@@ -150,12 +151,28 @@ __device__ __forceinline__ float sdf_from_signed_d2(int32_t s, double res)
     return s < 0 ? -f : f;
 }
 
+// lut[m] = (float)(sqrt((double)m) * res) for m < n: the exact value the combine loop stores (sdf_generation.hpp:254-265),
+// tabulated once per resolution so the final pass replaces ~25 FP64 issue slots per voxel by one cached 4-byte load.
+__global__ void __launch_bounds__(256) sqrt_lut_kernel(float* __restrict__ lut, int n, double res)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n) lut[m] = (float)(sqrt((double)m) * res);
+}
+
 template <int LOGB, int LPC, bool FINAL>
-__global__ void __launch_bounds__(32 * LPC) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
+__global__ void __launch_bounds__(32 * LPC, (LPC == 16 && LOGB == 5) ? 3 : 1) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
                                                                  int64_t line_stride, int64_t ncols,
-                                                                 int64_t outer_stride, double res, int* __restrict__ ext)
+                                                                 int64_t outer_stride, double res, int* __restrict__ ext,
+                                                                 long long* __restrict__ dbg,
+                                                                 const float* __restrict__ lut, int lut_n)
 {
     using BH = BandHull<LOGB, LPC>;
+    // optional phase clocks (diagnostics): thread 0 of the first 1024 CTAs stores clock64() at phase boundaries
+    const unsigned dbg_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned dbg_stride = (gridDim.x * gridDim.y + 1023u) / 1024u;            // sample ~1024 CTAs evenly
+    const int dbg_cta = (int)(dbg_lin / dbg_stride);
+    const bool dbg_on = dbg != nullptr && threadIdx.x == 0 && (dbg_lin % dbg_stride) == 0 && dbg_cta < 1024;
+    if (dbg_on) dbg[dbg_cta * 8 + 0] = clock64();
     constexpr int B = BH::B;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BandTile T;
@@ -177,37 +194,55 @@ __global__ void __launch_bounds__(32 * LPC) band_strided_kernel(int32_t* __restr
 
     typename BH::pcw_t Pw, PCw;
     {
-        int32_t in[B];
+        // stage the band's values into its own stack slots (the hull is then built in place)
+        const bh_addr_t slot0 = T.S + 4u * (uint32_t)BH::sidx(b, 0, c);
+        constexpr int U = 8;
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const int q = base + i;
-            in[i] = (col_ok && q < n) ? gc[(int64_t)q * line_stride] : SDF_INF;
+        for (int i0 = 0; i0 < B; i0 += U) {
+            int32_t tmp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + i0 + u;
+                tmp[u] = (col_ok && q < n) ? gc[(int64_t)q * line_stride] : SDF_INF;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) bh_st32(slot0 + (uint32_t)((i0 + u) * (LPC * 4)), (uint32_t)tmp[u]);
         }
         bool prevpol = false;
         if (col_ok) {
             const int qp = b > 0 ? base - 1 : 0;
             prevpol = gc[(int64_t)qp * line_stride] < 0;
         }
-        BH::build(T, c, b, col_ok ? n : 0, in, prevpol, Pw, PCw);
+        if (dbg_on) dbg[dbg_cta * 8 + 1] = clock64();
+        BH::build(T, c, b, col_ok ? n : 0, prevpol, Pw, PCw);
     }
+    if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
     __syncthreads();
+    if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
     for (int lv = 0; lv < nlevels; ++lv) {
         BH::merge(T, c, b, nb, lv);
         __syncthreads();
     }
+    if (dbg_on) dbg[dbg_cta * 8 + 4] = clock64();
     int32_t maxpos = 0, maxneg = 0;
     if (col_ok) {
+        int32_t* dst = gc + (int64_t)base * line_stride;
         BH::query(T, c, b, nb, n, nlevels, Pw, PCw, [&](int i, int32_t v) {
-            int32_t* dst = gc + (int64_t)(base + i) * line_stride;
+            (void)i;
             if (FINAL) {
-                if (v > maxpos) maxpos = v;
-                if (-v > maxneg) maxneg = -v;
-                *dst = __float_as_int(sdf_from_signed_d2(v, res));
+                const int32_t m = v < 0 ? -v : v;
+                if (v < 0) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);
+                float f;
+                if (m < lut_n) f = __ldg(lut + m);
+                else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+                *dst = __float_as_int(v < 0 ? -f : f);
             } else {
                 *dst = v;
             }
+            dst += line_stride;
         });
     }
+    if (dbg_on) dbg[dbg_cta * 8 + 5] = clock64();
     if (FINAL) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -231,6 +266,13 @@ cudaError_t launch_pack_cells(const void* d_cells, int64_t n, int unknown_is_fil
     return cudaGetLastError();
 }
 
+cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    sqrt_lut_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_lut, n, res);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, cudaStream_t st)
 {
     if (nz > 2048) return cudaErrorInvalidValue;
@@ -243,7 +285,8 @@ cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64
 
 template <int LOGB, int LPC, bool FINAL>
 static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                   int64_t outer_stride, double res, int* ext, cudaStream_t st)
+                                   int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
+                                   cudaStream_t st)
 {
     constexpr int B = 1 << LOGB;
     const int nb = (n + B - 1) / B;
@@ -254,25 +297,33 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
         if (e != cudaSuccess) return e;
     }
     dim3 grid((unsigned)((ncols + LPC - 1) / LPC), (unsigned)nouter);
-    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext);
+    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n);
     return cudaGetLastError();
 }
 
 template <bool FINAL>
 static cudaError_t launch_band_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                 int64_t outer_stride, double res, int* ext, cudaStream_t st)
+                                 int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
+                                   cudaStream_t st)
 {
-    if (n <= 256) return launch_band_cfg<5, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, st);
-    if (n <= 1024) return launch_band_cfg<5, 16, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, st);
-    if (n <= 2048) return launch_band_cfg<6, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, st);
+    if (n <= 256) return launch_band_cfg<5, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    if (n <= 1024) {
+        static int lpc = -1;                      // tuning knob (SDF_B200_LPC=8|16|32), default 16
+        if (lpc < 0) { const char* e = getenv("SDF_B200_LPC"); lpc = e ? atoi(e) : 16; }
+        if (lpc == 8) return launch_band_cfg<5, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+        if (lpc == 32) return launch_band_cfg<5, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+        return launch_band_cfg<5, 16, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    }
+    if (n <= 2048) return launch_band_cfg<6, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                int64_t outer_stride, bool final_pass, double res, int* d_ext, cudaStream_t st)
+                                int64_t outer_stride, bool final_pass, double res, int* d_ext, long long* d_dbg,
+                                const float* d_lut, int lut_n, cudaStream_t st)
 {
-    return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, st)
-                      : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, st);
+    return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
+                      : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
 }
 
 }  // namespace sdfb200

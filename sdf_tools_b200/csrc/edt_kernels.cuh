@@ -15,6 +15,10 @@ cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64
 //        final_pass: also apply (float)(sqrt((double)d2)*res) with the polarity sign and reduce the
 //        per-polarity maxima of d2 into d_ext[0..1].
 cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                int64_t outer_stride, bool final_pass, double res, int* d_ext, cudaStream_t st);
+                                int64_t outer_stride, bool final_pass, double res, int* d_ext, long long* d_dbg,
+                                const float* d_lut, int lut_n, cudaStream_t st);
+
+// d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution
+cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st);   // d_dbg: optional 2 x 1024 x 8 phase clocks (diagnostics), or NULL
 
 }  // namespace sdfb200

@@ -1,6 +1,7 @@
 // tests/emul/emul_band.cpp -- CPU emulation of the band-per-warp / line-per-lane phases in
 // sdf_tools_b200/csrc/band_hull.cuh.  Test infrastructure: runs the SAME phase functions the CUDA kernel calls,
 // as plain loops over the (line, band) threads of a tile (optionally in shuffled order, to expose races inside a phase).
+#define BH_COUNT 1
 #include "../../sdf_tools_b200/csrc/band_hull.cuh"
 #include <vector>
 #include <algorithm>
@@ -31,14 +32,16 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
         shuf();
         for (int t : order) {
             const int b = t / LPC, c = t % LPC;
-            int32_t in[B];
             bool prevpol = false;
+            for (int i = 0; i < B; i++) {
+                const int q = b * B + i;
+                S[(size_t)BH::sidx(b, i, c)] = (c0 + c < ncols && q < n) ? (uint32_t)g[(int64_t)q * line_stride + c0 + c] : (uint32_t)SDF_INF;
+            }
             if (c0 + c < ncols) {
-                for (int i = 0; i < B; i++) { const int q = b * B + i; in[i] = q < n ? g[(int64_t)q * line_stride + c0 + c] : SDF_INF; }
                 const int qp = b > 0 ? b * B - 1 : 0;
                 prevpol = (qp < n) ? g[(int64_t)qp * line_stride + c0 + c] < 0 : false;
-            } else { for (int i = 0; i < B; i++) in[i] = SDF_INF; }
-            BH::build(T, c, b, (c0 + c < ncols) ? n : 0, in, prevpol, Pw[t], PCw[t]);
+            }
+            BH::build(T, c, b, (c0 + c < ncols) ? n : 0, prevpol, Pw[t], PCw[t]);
         }
         for (int lv = 0; lv < nlevels; lv++) { shuf(); for (int t : order) BH::merge(T, t % LPC, t / LPC, nb, lv); }
         shuf();
@@ -61,6 +64,8 @@ static int dispatch(int32_t* g, int n, int64_t ls, int64_t ncols, int shuffle, i
 }
 
 extern "C" {
+
+void emul_band_counters(long long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = bh_counters[i]; if (reset) bh_counters[i] = 0; } }
 
 int emul_band_pass(int32_t* g, int n, int64_t line_stride, int64_t ncols, int logb, int lpc, int shuffle, uint64_t seed)
 {
