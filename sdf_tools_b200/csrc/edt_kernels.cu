@@ -48,32 +48,61 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const float2* __restric
 
 // ============================================================================================ K1 binary z
 // One warp per contiguous z line.  Occupancy bytes are gathered with coalesced 1-byte loads + ballot into one
-// 32-bit word per lane, run boundaries are found with bit operations and two warp-level carries, and
-//   s(z) = +-min(z-a+1, e-z)^2   ([a,e) = the run of equal polarity around z)
-// is written back 32 positions at a time (128-byte coalesced rows).
+// 32-bit word per lane (lane l = positions 32l..32l+31); run boundaries come from bit operations and two warp-level
+// carries; every lane then walks its own 32 positions with two counters,
+//   s(z) = +-min(z-a+1, e-z)^2   ([a,e) = the run of equal polarity around z),
+// and the 32x32 block is transposed through a padded shared-memory tile so rows leave as 128-byte coalesced stores.
 template <int WPL>   // words (of 32 positions) per lane: 1 for nz <= 1024, 2 for nz <= 2048
 __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ out,
                                                        int nz, int64_t nlines)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int32_t tile_all[8][32 * 33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (line >= nlines) return;
+    int32_t* tile = tile_all[wib];
     const uint8_t* mp = mask + line * nz;
     int32_t* op = out + line * nz;
     const int nw = (nz + 31) >> 5;
+    constexpr int FARB = 40000;                 // "no zero site on this side"
     uint32_t P[WPL], PC[WPL];
     int a_in[WPL], e_in[WPL];
+    const bool vec16 = ((nz & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);   // warp-uniform
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
         uint32_t mine = 0;
+        if (vec16) {
+            // two 16-byte loads per lane cover 1024 positions; 16 occupancy bits per load, regrouped by shuffles
+            uint32_t half[2];
+#pragma unroll
+            for (int hs = 0; hs < 2; ++hs) {
+                const int byte0 = (k * 2 + hs) * 512 + lane * 16;
+                uint32_t hbits = 0;
+                if (byte0 < nz) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(mp + byte0));
+                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t t = __vcmpne4(xs[q], 0u) & 0x01010101u;      // 1 per non-zero byte
+                        hbits |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+                    }
+                }
+                half[hs] = hbits;
+            }
+            const int src = (lane & 15) * 2;
+            const uint32_t a0 = __shfl_sync(0xffffffffu, half[0], src), b0 = __shfl_sync(0xffffffffu, half[0], src + 1);
+            const uint32_t a1 = __shfl_sync(0xffffffffu, half[1], src), b1 = __shfl_sync(0xffffffffu, half[1], src + 1);
+            mine = (lane < 16) ? (a0 | (b0 << 16)) : (a1 | (b1 << 16));
+        } else {
 #pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-            const int w = k * 32 + i;
-            if (w < nw) {                       // warp-uniform
-                const int z = w * 32 + lane;
-                const bool f = (z < nz) ? (__ldg(mp + z) != 0) : false;
-                const uint32_t bal = __ballot_sync(0xffffffffu, f);
-                if (lane == i) mine = bal;
+            for (int i = 0; i < 32; ++i) {
+                const int w = k * 32 + i;
+                if (w < nw) {                       // warp-uniform
+                    const int z = w * 32 + lane;
+                    const bool f = (z < nz) ? (__ldg(mp + z) != 0) : false;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, f);
+                    if (lane == i) mine = bal;
+                }
             }
         }
         P[k] = mine;
@@ -91,7 +120,6 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
         const int valid = nz - w * 32;
         if (valid < 32) pc &= (valid > 0) ? ((1u << valid) - 1u) : 0u;
         PC[k] = pc;
-        // a_in: last run start in words before this one
         const uint32_t bal = __ballot_sync(0xffffffffu, pc != 0);
         const int myhi = pc ? (w * 32 + 31 - __clz((int)pc)) : -1;
         const uint32_t lower = bal & ((1u << lane) - 1u);
@@ -115,26 +143,34 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
         const int blk_first = bal ? __shfl_sync(0xffffffffu, mylo, __ffs((int)bal) - 1) : nz;
         if (blk_first < nz) next_run_start = blk_first;
     }
-    const uint32_t le = (2u << lane) - 1u;      // bits <= lane
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int w = k * 32 + i;
-            if (w < nw) {
-                const uint32_t p = __shfl_sync(0xffffffffu, P[k], i);
-                const uint32_t pc = __shfl_sync(0xffffffffu, PC[k], i);
-                const int ai = __shfl_sync(0xffffffffu, a_in[k], i);
-                const int ei = __shfl_sync(0xffffffffu, e_in[k], i);
-                const int z = w * 32 + lane;
-                const uint32_t mle = pc & le, mgt = pc & ~le;
-                const int a = mle ? (w * 32 + 31 - __clz((int)mle)) : ai;
-                const int e = mgt ? (w * 32 + __ffs((int)mgt) - 1) : ei;
-                int32_t best = SDF_INF;
-                if (a >= 1) { const int d = z - a + 1; best = d * d; }
-                if (e < nz) { const int d = e - z; const int32_t q = d * d; best = q < best ? q : best; }
-                if (z < nz) op[z] = ((p >> lane) & 1u) ? -best : best;
+        if (k * 32 < nw) {                      // warp-uniform
+            const int z0 = (k * 32 + lane) * 32;
+            const uint32_t p = P[k], pc = PC[k];
+            int dl = (a_in[k] >= 1) ? (z0 - a_in[k] + 1) : FARB;                  // z - a + 1
+            int e = (pc & ~1u) ? (z0 + __ffs((int)(pc & ~1u)) - 1) : e_in[k];     // first run start after z0
+            int dr = (e < nz) ? (e - z0) : FARB;                                  // e - z
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if ((pc >> j) & 1u) {           // a run starts here
+                    dl = 1;
+                    const uint32_t rest = (j < 31) ? (pc >> (j + 1)) : 0u;
+                    e = rest ? (z0 + j + __ffs((int)rest)) : e_in[k];
+                    dr = (e < nz) ? (e - z0 - j) : FARB;
+                }
+                const int d = dl < dr ? dl : dr;
+                const int32_t v = (d >= FARB) ? SDF_INF : d * d;
+                tile[lane * 33 + j] = ((p >> j) & 1u) ? -v : v;
+                ++dl; --dr;
             }
+            __syncwarp();
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const int z = (k * 32 + r) * 32 + lane;
+                if (z < nz) op[z] = tile[r * 33 + lane];
+            }
+            __syncwarp();
         }
     }
 }
