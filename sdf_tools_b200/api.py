@@ -105,6 +105,29 @@ class Context:
         self._check(self._lib.sdf_b200_pack_cells_device(self._h, C.c_void_p(d_cells_ptr), n,
                                                          int(bool(unknown_is_filled)), C.c_void_p(d_mask_ptr)))
 
+    # ------------------------------------------------------------------------------------------ slab builds
+    def slab_summary_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, d_summary_ptr: int):
+        self._check(self._lib.sdf_b200_slab_summary_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz_local,
+                                                           C.c_void_p(d_summary_ptr)))
+
+    def slab_build_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, resolution: float,
+                          d_all_summaries_ptr: int, slab_widths, rank: int, d_sdf_ptr: int):
+        w = (C.c_int32 * len(slab_widths))(*[int(v) for v in slab_widths])
+        self._check(self._lib.sdf_b200_slab_build_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz_local,
+                                                         float(resolution), C.c_void_p(d_all_summaries_ptr), w,
+                                                         len(slab_widths), int(rank), C.c_void_p(d_sdf_ptr)))
+
+    def get_extrema_raw(self):
+        a, b = C.c_int32(), C.c_int32()
+        self._check(self._lib.sdf_b200_get_extrema_raw(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def extrema_from_raw(self, max_free_d2: int, max_filled_d2: int, resolution: float):
+        mx, mn = C.c_double(), C.c_double()
+        self._lib.sdf_b200_extrema_from_raw(int(max_free_d2), int(max_filled_d2), float(resolution),
+                                            C.byref(mx), C.byref(mn))
+        return mx.value, mn.value
+
     def get_extrema(self):
         mx, mn = C.c_double(), C.c_double()
         self._check(self._lib.sdf_b200_get_extrema(self._h, C.byref(mx), C.byref(mn)))

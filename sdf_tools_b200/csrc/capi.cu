@@ -15,6 +15,8 @@ struct sdf_b200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     int* d_ext = nullptr;              // [0] max +d2 over free voxels, [1] max d2 over filled voxels
+    void* d_carries = nullptr; size_t carries_bytes = 0;   // slab builds: int2 per z line
+    int* d_widths = nullptr;
     float* d_lut = nullptr;            // (float)(sqrt((double)m)*res) for m < LUT_N at resolution lut_res
     double lut_res = -1.0;
     long long* d_dbg = nullptr;        // optional phase clocks of the band kernels: [pass 2|3][1024 CTAs][8]
@@ -107,6 +109,8 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     if (ctx->d_ext) cudaFree(ctx->d_ext);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
+    if (ctx->d_carries) cudaFree(ctx->d_carries);
+    if (ctx->d_widths) cudaFree(ctx->d_widths);
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     if (ctx->d_out) cudaFree(ctx->d_out);
@@ -149,7 +153,7 @@ int sdf_b200_host_free(void* p)
 
 // mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in place in d_field
 static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz, double res,
-                      int32_t* d_field, bool final_pass)
+                      int32_t* d_field, bool final_pass, const void* d_carries = nullptr)
 {
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
@@ -164,7 +168,7 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[0], st), "event");
-    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, st), "launch binary_z");
+    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, d_carries, st), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
@@ -204,6 +208,68 @@ int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t 
     if (nx * ny * nz > 0 && (!d_mask || !d_out)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     return run_passes(ctx, d_mask, nx, ny, nz, 1.0, d_out, false);
+}
+
+int sdf_b200_slab_summary_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
+                                 uint32_t* d_summary)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz_local);
+    if (rc) return rc;
+    if (nx * ny * nz_local == 0) return SDF_B200_OK;
+    if (!d_mask || !d_summary) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(sdfb200::launch_slab_summary(d_mask, (int)nz_local, nx * ny, d_summary, ctx->stream), "launch slab_summary");
+    return SDF_B200_OK;
+}
+
+int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
+                               double resolution, const uint32_t* d_all_summaries, const int32_t* slab_widths,
+                               int nranks, int rank, float* d_sdf)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz_local);
+    if (rc) return rc;
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || !slab_widths)
+        return fail(ctx, SDF_B200_ERR_ARG, "bad rank / nranks / slab_widths");
+    const int64_t nlines = nx * ny;
+    if (nlines * nz_local > 0 && (!d_mask || !d_sdf || !d_all_summaries)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    const void* carries = nullptr;
+    if (nlines * nz_local > 0) {
+        if ((rc = grow(ctx, &ctx->d_carries, &ctx->carries_bytes, (size_t)nlines * 8))) return rc;
+        if (!ctx->d_widths) CK(cudaMalloc(&ctx->d_widths, 64 * sizeof(int)), "cudaMalloc(widths)");
+        CK(cudaMemcpyAsync(ctx->d_widths, slab_widths, (size_t)nranks * sizeof(int), cudaMemcpyHostToDevice, st), "H2D widths");
+        CK(sdfb200::launch_slab_carry(d_all_summaries, ctx->d_widths, nranks, rank, nlines, ctx->d_carries, st),
+           "launch slab_carry");
+        carries = ctx->d_carries;
+    }
+    rc = run_passes(ctx, d_mask, nx, ny, nz_local, resolution, reinterpret_cast<int32_t*>(d_sdf), true, carries);
+    if (rc == SDF_B200_OK && carries) ctx->launches++;
+    return rc;
+}
+
+int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_t* out_max_filled_d2)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    if (!ctx->built) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_get_extrema_raw: no finished build on this context");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    if (out_max_free_d2) *out_max_free_d2 = h[0];
+    if (out_max_filled_d2) *out_max_filled_d2 = h[1];
+    return SDF_B200_OK;
+}
+
+int sdf_b200_extrema_from_raw(int32_t max_free_d2, int32_t max_filled_d2, double resolution, double* out_max, double* out_min)
+{
+    const double inf = std::numeric_limits<double>::infinity();
+    auto dist = [&](int m) { return (m >= SDF_B200_INF) ? inf : sqrt((double)m) * resolution; };
+    if (out_max) *out_max = max_free_d2 > 0 ? dist(max_free_d2) : -inf;
+    if (out_min) *out_min = max_filled_d2 > 0 ? -dist(max_filled_d2) : inf;
+    return SDF_B200_OK;
 }
 
 int sdf_b200_get_extrema(sdf_b200_ctx* ctx, double* out_max, double* out_min)

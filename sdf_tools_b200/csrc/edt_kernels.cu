@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const float2* __restric
 // and the 32x32 block is transposed through a padded shared-memory tile so rows leave as 128-byte coalesced stores.
 template <int WPL>   // words (of 32 positions) per lane: 1 for nz <= 1024, 2 for nz <= 2048
 __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ out,
-                                                       int nz, int64_t nlines)
+                                                       int nz, int64_t nlines, const int2* __restrict__ carries)
 {
     __shared__ int32_t tile_all[8][32 * 33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -65,6 +65,9 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
     int32_t* op = out + line * nz;
     const int nw = (nz + 31) >> 5;
     constexpr int FARB = 40000;                 // "no zero site on this side"
+    // slab builds: distance from this line's first / last voxel to the nearest voxel of the other polarity in the
+    // slabs below / above (FARB if none); whole-grid builds: nothing beyond the faces
+    const int2 cy = carries ? __ldg(carries + line) : make_int2(FARB, FARB);
     uint32_t P[WPL], PC[WPL];
     int a_in[WPL], e_in[WPL];
     const bool vec16 = ((nz & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);   // warp-uniform
@@ -148,16 +151,16 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
         if (k * 32 < nw) {                      // warp-uniform
             const int z0 = (k * 32 + lane) * 32;
             const uint32_t p = P[k], pc = PC[k];
-            int dl = (a_in[k] >= 1) ? (z0 - a_in[k] + 1) : FARB;                  // z - a + 1
+            int dl = (a_in[k] >= 1) ? (z0 - a_in[k] + 1) : (cy.x < FARB ? z0 + cy.x : FARB);       // z - a + 1
             int e = (pc & ~1u) ? (z0 + __ffs((int)(pc & ~1u)) - 1) : e_in[k];     // first run start after z0
-            int dr = (e < nz) ? (e - z0) : FARB;                                  // e - z
+            int dr = (e < nz) ? (e - z0) : (cy.y < FARB ? nz - 1 - z0 + cy.y : FARB);              // e - z
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if ((pc >> j) & 1u) {           // a run starts here
                     dl = 1;
                     const uint32_t rest = (j < 31) ? (pc >> (j + 1)) : 0u;
                     e = rest ? (z0 + j + __ffs((int)rest)) : e_in[k];
-                    dr = (e < nz) ? (e - z0 - j) : FARB;
+                    dr = (e < nz) ? (e - z0 - j) : (cy.y < FARB ? nz - 1 - z0 - j + cy.y : FARB);
                 }
                 const int d = dl < dr ? dl : dr;
                 const int32_t v = (d >= FARB) ? SDF_INF : d * d;
@@ -173,6 +176,65 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
             __syncwarp();
         }
     }
+}
+
+// ===================================================================================== slab carries (multi-GPU)
+// The grid is cut into slabs along z (one per GPU).  The binary pass is the only one that crosses the cut, and all
+// it needs from the other slabs is, per z line, the distance from the slab face to the nearest voxel of the other
+// polarity.  Each rank publishes per line  {polarity of its first voxel, length of the leading run,
+// polarity of its last voxel, length of the trailing run}  (4 bytes); after one all-gather every rank resolves its
+// own carries locally, also across slabs that are a single run.
+__global__ void __launch_bounds__(256) slab_summary_kernel(const uint8_t* __restrict__ mask, int nz, int64_t nlines,
+                                                           uint32_t* __restrict__ summary)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (line >= nlines) return;
+    const uint8_t* mp = mask + line * nz;
+    const bool first = __ldg(mp) != 0, last = __ldg(mp + nz - 1) != 0;
+    int lead = nz, trail = nz;                        // warp-wide min of the first / last position that differs
+    for (int z = lane; z < nz; z += 32) {
+        const bool f = __ldg(mp + z) != 0;
+        if (f != first && z < lead) lead = z;
+        if (f != last && (nz - 1 - z) < trail) trail = nz - 1 - z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
+        trail = min(trail, __shfl_xor_sync(0xffffffffu, trail, o));
+    }
+    if (lane == 0)
+        summary[line] = (uint32_t)lead | ((uint32_t)first << 15) | ((uint32_t)trail << 16) | ((uint32_t)last << 31);
+}
+
+// all[r * nlines + line] = summary of rank r; widths[r] = slab thickness of rank r.
+__global__ void __launch_bounds__(256) slab_carry_kernel(const uint32_t* __restrict__ all, const int* __restrict__ widths,
+                                                         int nranks, int rank, int64_t nlines, int2* __restrict__ carries)
+{
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= nlines) return;
+    constexpr int FARB = 40000;
+    const uint32_t me = all[(int64_t)rank * nlines + line];
+    const bool myfirst = (me >> 15) & 1u, mylast = (me >> 31) & 1u;
+    int cl = FARB, cr = FARB, acc = 0;
+    for (int k = rank - 1; k >= 0; --k) {             // towards lower z
+        const uint32_t s = all[(int64_t)k * nlines + line];
+        const bool klast = (s >> 31) & 1u;
+        const int ktrail = (int)((s >> 16) & 0x7fffu), w = widths[k];
+        if (klast != myfirst) { cl = acc + 1; break; }
+        if (ktrail < w) { cl = acc + ktrail + 1; break; }
+        acc += w;
+    }
+    acc = 0;
+    for (int k = rank + 1; k < nranks; ++k) {         // towards higher z
+        const uint32_t s = all[(int64_t)k * nlines + line];
+        const bool kfirst = (s >> 15) & 1u;
+        const int klead = (int)(s & 0x7fffu), w = widths[k];
+        if (kfirst != mylast) { cr = acc + 1; break; }
+        if (klead < w) { cr = acc + klead + 1; break; }
+        acc += w;
+    }
+    carries[line] = make_int2(cl < FARB ? cl : FARB, cr < FARB ? cr : FARB);
 }
 
 // ========================================================================================= K2/K3 band hull
@@ -309,13 +371,30 @@ cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, cudaStream_t st)
+cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, const void* d_carries,
+                            cudaStream_t st)
 {
     if (nz > 2048) return cudaErrorInvalidValue;
     const int wpb = 8;
     const unsigned blocks = (unsigned)((nlines + wpb - 1) / wpb);
-    if (nz <= 1024) binary_z_kernel<1><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines);
-    else binary_z_kernel<2><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines);
+    const int2* cy = reinterpret_cast<const int2*>(d_carries);
+    if (nz <= 1024) binary_z_kernel<1><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines, cy);
+    else binary_z_kernel<2><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines, cy);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slab_summary(const uint8_t* d_mask, int nz, int64_t nlines, uint32_t* d_summary, cudaStream_t st)
+{
+    const int wpb = 8;
+    slab_summary_kernel<<<(unsigned)((nlines + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_mask, nz, nlines, d_summary);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slab_carry(const uint32_t* d_all, const int* d_widths, int nranks, int rank, int64_t nlines,
+                              void* d_carries, cudaStream_t st)
+{
+    slab_carry_kernel<<<(unsigned)((nlines + 255) / 256), 256, 0, st>>>(d_all, d_widths, nranks, rank, nlines,
+                                                                        reinterpret_cast<int2*>(d_carries));
     return cudaGetLastError();
 }
 

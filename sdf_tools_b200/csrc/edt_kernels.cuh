@@ -9,7 +9,16 @@ namespace sdfb200 {
 cudaError_t launch_pack_cells(const void* d_cells, int64_t n, int unknown_is_filled, uint8_t* d_mask, cudaStream_t st);
 
 // K1: binary pass along the contiguous z axis.  mask[nlines][nz] -> signed int32 d^2 along z
-cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, cudaStream_t st);
+//     d_carries: NULL, or per line {distance from z=0 / z=nz-1 to the nearest other-polarity voxel in the slabs
+//     below / above} (int2, 40000 = none) for slab builds.
+cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, const void* d_carries,
+                            cudaStream_t st);
+
+// Slab (multi-GPU) support for the binary pass: per-line 4-byte summary of one slab, and the resolution of one
+// rank's carries from the all-gathered summaries of every rank (d_all[r*nlines + line], d_widths[r]).
+cudaError_t launch_slab_summary(const uint8_t* d_mask, int nz, int64_t nlines, uint32_t* d_summary, cudaStream_t st);
+cudaError_t launch_slab_carry(const uint32_t* d_all, const int* d_widths, int nranks, int rank, int64_t nlines,
+                              void* d_carries, cudaStream_t st);
 
 // K2/K3: in-place envelope pass along a strided axis: nouter blocks of n rows x ncols contiguous columns.
 //        final_pass: also apply (float)(sqrt((double)d2)*res) with the polarity sign and reduce the

@@ -1,0 +1,160 @@
+"""sdf_tools_b200/distributed.py -- slab-sharded SDF build: one process per GPU, the grid cut along z.
+
+The reference is single-process; this is the scale-out of its hot path (`ExtractSignedDistanceField`,
+sdf_generation.hpp:209-271) that BASELINE.json asks for.  Only the first (binary) pass runs along z, so the only
+thing that crosses a cut is, per z line, the distance from the slab face to the nearest voxel of the other
+polarity.  Protocol per build (include/sdf_b200.h "Slab builds"):
+
+  1. every rank summarises its slab: per (x,y) line  {polarity of first voxel, leading-run length,
+     polarity of last voxel, trailing-run length}  packed in 4 bytes            (sdf_b200_slab_summary_device)
+  2. ONE all-gather of the summaries (nx*ny*4 bytes per rank; NCCL over NVLink)  -- the only data-path collective
+  3. every rank resolves its carries locally (also across slabs that are a single run) and runs the three passes
+     on its own slab                                                             (sdf_b200_slab_build_device)
+  4. all-reduce(max) of two integers gives the global (max, min) pair of sdf_generation.hpp:269.
+
+The numpy functions below restate steps 1-3 for the world_size-2 gloo tests on CPU (host-side protocol logic);
+the CUDA kernels in csrc/edt_kernels.cu are what runs in production.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FARB = 40000          # "no voxel of the other polarity on this side" (matches the kernels)
+INF = 0x40000000
+
+
+def slab_ranges(nz: int, nranks: int, align: int = 16):
+    """Balanced z ranges [z0, z1) per rank, cut at multiples of `align` where possible (16-byte mask loads)."""
+    if nranks < 1:
+        raise ValueError("nranks must be >= 1")
+    units = nz // align
+    if units >= nranks:
+        base, extra = divmod(units, nranks)
+        widths = [(base + (1 if r < extra else 0)) * align for r in range(nranks)]
+        widths[-1] += nz - sum(widths)
+    else:
+        base, extra = divmod(nz, nranks)
+        widths = [base + (1 if r < extra else 0) for r in range(nranks)]
+    out, z = [], 0
+    for w in widths:
+        out.append((z, z + w))
+        z += w
+    return out
+
+
+# ------------------------------------------------------------------------------ numpy restatement of the protocol
+def summary_np(mask_slab: np.ndarray) -> np.ndarray:
+    """uint32 (nx, ny): lead | first<<15 | trail<<16 | last<<31 per z line of a (nx, ny, nzl) slab."""
+    m = mask_slab != 0
+    nzl = m.shape[2]
+    first, last = m[:, :, 0], m[:, :, -1]
+    diff_f = m != first[:, :, None]
+    diff_l = m != last[:, :, None]
+    lead = np.where(diff_f.any(axis=2), diff_f.argmax(axis=2), nzl)
+    trail = np.where(diff_l.any(axis=2), diff_l[:, :, ::-1].argmax(axis=2), nzl)
+    return (lead.astype(np.uint32) | (first.astype(np.uint32) << 15) | (trail.astype(np.uint32) << 16)
+            | (last.astype(np.uint32) << 31))
+
+
+def resolve_carries_np(all_summaries: np.ndarray, widths, rank: int):
+    """(carry_lo, carry_hi) int32 (nx, ny): distance from this rank's first / last voxel of every line to the
+    nearest voxel of the other polarity in lower / higher slabs (FARB if none)."""
+    me = all_summaries[rank]
+    myfirst, mylast = (me >> 15) & 1, (me >> 31) & 1
+    shape = me.shape
+    cl = np.full(shape, FARB, np.int64)
+    cr = np.full(shape, FARB, np.int64)
+    acc = np.zeros(shape, np.int64)
+    open_ = np.ones(shape, bool)
+    for k in range(rank - 1, -1, -1):
+        s = all_summaries[k]
+        klast, ktrail, w = (s >> 31) & 1, (s >> 16) & 0x7FFF, int(widths[k])
+        hit1 = open_ & (klast != myfirst)
+        cl[hit1] = acc[hit1] + 1
+        open_ &= ~hit1
+        hit2 = open_ & (ktrail < w)
+        cl[hit2] = acc[hit2] + ktrail[hit2] + 1
+        open_ &= ~hit2
+        acc[open_] += w
+    acc[:] = 0
+    open_[:] = True
+    for k in range(rank + 1, len(widths)):
+        s = all_summaries[k]
+        kfirst, klead, w = (s >> 15) & 1, s & 0x7FFF, int(widths[k])
+        hit1 = open_ & (kfirst != mylast)
+        cr[hit1] = acc[hit1] + 1
+        open_ &= ~hit1
+        hit2 = open_ & (klead < w)
+        cr[hit2] = acc[hit2] + klead[hit2] + 1
+        open_ &= ~hit2
+        acc[open_] += w
+    return np.minimum(cl, FARB).astype(np.int32), np.minimum(cr, FARB).astype(np.int32)
+
+
+def binary_z_np(mask_slab: np.ndarray, carry_lo=None, carry_hi=None) -> np.ndarray:
+    """Signed squared distance along z to the nearest voxel of the other polarity (the binary pass), with the
+    optional slab carries.  int32 (nx, ny, nzl), +-INF where there is none."""
+    m = mask_slab != 0
+    nzl = m.shape[2]
+    idx = np.arange(nzl, dtype=np.int64)
+    change = np.zeros(m.shape, bool)
+    change[:, :, 1:] = m[:, :, 1:] != m[:, :, :-1]
+    start = np.maximum.accumulate(np.where(change, idx, -1), axis=2)                       # run start or -1
+    nxt = np.where(change, idx, 10 ** 9)
+    nxt = np.minimum.accumulate(nxt[:, :, ::-1], axis=2)[:, :, ::-1]
+    nxt_after = np.concatenate([nxt[:, :, 1:], np.full(m.shape[:2] + (1,), 10 ** 9)], axis=2)   # first run start > z
+    lo = FARB if carry_lo is None else carry_lo[:, :, None].astype(np.int64)
+    hi = FARB if carry_hi is None else carry_hi[:, :, None].astype(np.int64)
+    dl = np.where(start >= 1, idx - start + 1, np.where(np.asarray(lo) < FARB, idx + lo, FARB))
+    dr = np.where(nxt_after < nzl, nxt_after - idx, np.where(np.asarray(hi) < FARB, nzl - 1 - idx + hi, FARB))
+    d = np.minimum(dl, dr)
+    d2 = np.where(d >= FARB, INF, d * d)
+    return np.where(m, -d2, d2).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------ device path
+class SlabBuilder:
+    """One rank of a slab-sharded build.  `group` is a torch.distributed process group (NCCL on GPUs)."""
+
+    def __init__(self, ctx, shape, rank: int, world: int, group=None):
+        import torch
+        self.torch = torch
+        self.ctx = ctx
+        self.nx, self.ny, self.nz = (int(v) for v in shape)
+        self.rank, self.world, self.group = rank, world, group
+        self.ranges = slab_ranges(self.nz, world)
+        self.widths = [b - a for a, b in self.ranges]
+        self.z0, self.z1 = self.ranges[rank]
+        self.nzl = self.z1 - self.z0
+        dev = torch.device("cuda", ctx.device)
+        nl = self.nx * self.ny
+        self.summary = torch.empty(nl, dtype=torch.int32, device=dev)
+        self.all_summaries = torch.empty(world * nl, dtype=torch.int32, device=dev)
+        self.raw = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def build(self, d_mask, resolution: float, d_sdf):
+        """d_mask: uint8 (nx, ny, nzl) device tensor of this rank's slab; d_sdf: float32 tensor of the same shape."""
+        torch = self.torch
+        import torch.distributed as dist
+        ctx = self.ctx
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.slab_summary_device(d_mask.data_ptr(), self.nx, self.ny, self.nzl, self.summary.data_ptr())
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.all_summaries, self.summary, group=self.group)
+            src = self.all_summaries
+        else:
+            src = self.summary
+        ctx.slab_build_device(d_mask.data_ptr(), self.nx, self.ny, self.nzl, resolution, src.data_ptr(),
+                              self.widths, self.rank, d_sdf.data_ptr())
+        return d_sdf
+
+    def extrema(self, resolution: float):
+        """Global (max, min): all-reduce(max) of the two raw integers, then the f64 conversion."""
+        torch = self.torch
+        import torch.distributed as dist
+        a, b = self.ctx.get_extrema_raw()
+        if self.world > 1:
+            t = torch.tensor([a, b], dtype=torch.int32, device=self.raw.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            a, b = (int(v) for v in t.tolist())
+        return self.ctx.extrema_from_raw(a, b, resolution)

@@ -53,9 +53,11 @@ def sphere(shape, radius_frac: float = 0.3) -> np.ndarray:
     return ((x * x + y * y + z * z) <= r * r).astype(np.uint8)
 
 
-def pointcloud(shape, n_points: int, seed: int, n_boxes: int = 64, ground_z: int = 8) -> np.ndarray:
-    """Voxelised synthetic point cloud: points uniform (by area) on box faces and a ground plane."""
+def pointcloud(shape, n_points: int, seed: int, n_boxes: int = 64, ground_z: int = 8, zrange=None) -> np.ndarray:
+    """Voxelised synthetic point cloud: points uniform (by area) on box faces and a ground plane.
+    zrange = (z0, z1): return only that z slab, shape (nx, ny, z1 - z0), without building the whole grid."""
     nx, ny, nz = shape
+    z0, z1 = (0, nz) if zrange is None else zrange
     dims = np.array([nx, ny, nz], dtype=np.float64)
     scale = min(nx, ny, nz) / 1024.0
     b = np.arange(n_boxes, dtype=np.uint64)
@@ -66,7 +68,7 @@ def pointcloud(shape, n_points: int, seed: int, n_boxes: int = 64, ground_z: int
     fa = np.stack([edge[:, 1] * edge[:, 2], edge[:, 0] * edge[:, 2], edge[:, 0] * edge[:, 1]], axis=1)  # normal x,y,z
     areas = np.concatenate([np.repeat(fa.reshape(-1), 2), [float(nx) * ny]])      # 6 per box + ground
     cdf = np.cumsum(areas) / areas.sum()
-    mask = np.zeros(shape, dtype=np.uint8)
+    mask = np.zeros((nx, ny, z1 - z0), dtype=np.uint8)
     step = 1 << 22
     for s in range(0, n_points, step):
         idx = np.arange(s, min(n_points, s + step), dtype=np.uint64)
@@ -90,7 +92,9 @@ def pointcloud(shape, n_points: int, seed: int, n_boxes: int = 64, ground_z: int
         pts[ground, 2] = min(ground_z, nz - 1) + 0.5
         ijk = np.floor(pts).astype(np.int64)
         np.clip(ijk, 0, np.array([nx - 1, ny - 1, nz - 1]), out=ijk)
-        mask[ijk[:, 0], ijk[:, 1], ijk[:, 2]] = 1
+        keep = (ijk[:, 2] >= z0) & (ijk[:, 2] < z1)
+        ijk = ijk[keep]
+        mask[ijk[:, 0], ijk[:, 1], ijk[:, 2] - z0] = 1
     return mask
 
 
@@ -144,22 +148,26 @@ CONFIGS = {
 }
 
 
-def make_mask(name: str, shape=None) -> np.ndarray:
-    """uint8 mask of a named config (optionally at another shape, e.g. scaled-down copies for tests)."""
+def make_mask(name: str, shape=None, zrange=None) -> np.ndarray:
+    """uint8 mask of a named config (optionally at another shape, e.g. scaled-down copies for tests).
+    zrange = (z0, z1) returns only that z slab (nx, ny, z1 - z0) -- what one rank of a slab build holds."""
     cfg = CONFIGS[name]
     shape = tuple(shape or cfg["shape"])
-    if name == "c1":
-        return iid(shape, 0.30, 1)
-    if name == "c2":
-        return sphere(shape, 0.3)
     if name == "c3":
-        return pointcloud(shape, int(2e6 * (np.prod(shape) / 1024.0 ** 3) ** (2.0 / 3.0)), 3)
+        return pointcloud(shape, int(2e6 * (np.prod(shape) / 1024.0 ** 3) ** (2.0 / 3.0)), 3, zrange=zrange)
     if name == "c4":
-        return pointcloud(shape, int(8e6 * (np.prod(shape) / (2048.0 * 2048 * 1024)) ** (2.0 / 3.0)), 4)
-    if name == "c5":
-        occ = octree(shape, 0.30, 5)
-        return (occ > 0.5).astype(np.uint8)
-    raise KeyError(name)
+        return pointcloud(shape, int(8e6 * (np.prod(shape) / (2048.0 * 2048 * 1024)) ** (2.0 / 3.0)), 4, zrange=zrange)
+    if name == "c1":
+        full = iid(shape, 0.30, 1)
+    elif name == "c2":
+        full = sphere(shape, 0.3)
+    elif name == "c5":
+        full = (octree(shape, 0.30, 5) > 0.5).astype(np.uint8)
+    else:
+        raise KeyError(name)
+    if zrange is not None:
+        full = np.ascontiguousarray(full[:, :, zrange[0]:zrange[1]])
+    return full
 
 
 # --------------------------------------------------------------------- fixture geometries of the reference's tests

@@ -127,3 +127,34 @@ def test_cells_entry_point(ctx):
 def test_point_cloud_256(ctx):
     mask = synth.make_mask("c3", (256, 256, 256))
     check_full(ctx, mask, 0.01)
+
+
+def test_slab_builds_on_one_gpu(ctx):
+    """The multi-GPU protocol, emulated on one device: N z slabs built one after the other through the slab C ABI
+    (summary -> gathered summaries -> slab build) must reproduce the single-grid build bit for bit."""
+    from sdf_tools_b200.distributed import slab_ranges
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    cases = [(synth.make_mask("c3", (96, 80, 128)), 4), (synth.iid((40, 33, 64), 0.3, 5), 3),
+             (synth.iid((17, 9, 50), 0.02, 6), 5), (np.zeros((8, 8, 32), np.uint8), 2)]
+    uni = synth.iid((24, 20, 96), 0.05, 9)
+    uni[:, :, 32:64] = uni[:, :, 32:33]            # a slab that is a single run on every line
+    cases.append((uni, 3))
+    for mask, nr in cases:
+        nx, ny, nz = mask.shape
+        want, (wmx, wmn) = ctx.build_from_mask(mask, 0.05)
+        ranges = slab_ranges(nz, nr)
+        widths = [b - a for a, b in ranges]
+        slabs = [torch.from_numpy(np.ascontiguousarray(mask[:, :, a:b])).cuda() for a, b in ranges]
+        allsum = torch.empty(nr * nx * ny, dtype=torch.int32, device="cuda")
+        for r, s in enumerate(slabs):
+            ctx.slab_summary_device(s.data_ptr(), nx, ny, widths[r], allsum[r * nx * ny:].data_ptr())
+        outs, raws = [], []
+        for r, s in enumerate(slabs):
+            o = torch.empty((nx, ny, widths[r]), dtype=torch.float32, device="cuda")
+            ctx.slab_build_device(s.data_ptr(), nx, ny, widths[r], 0.05, allsum.data_ptr(), widths, r, o.data_ptr())
+            raws.append(ctx.get_extrema_raw())
+            outs.append(o.cpu().numpy())
+        got = np.concatenate(outs, axis=2)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"slab build differs ({mask.shape}, {nr} slabs)"
+        mx, mn = ctx.extrema_from_raw(max(a for a, _ in raws), max(b for _, b in raws), 0.05)
+        assert (mx, mn) == (wmx, wmn)
