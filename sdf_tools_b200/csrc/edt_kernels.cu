@@ -47,134 +47,127 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const float2* __restric
 }
 
 // ============================================================================================ K1 binary z
-// One warp per contiguous z line.  Occupancy bytes are gathered with coalesced 1-byte loads + ballot into one
-// 32-bit word per lane (lane l = positions 32l..32l+31); run boundaries come from bit operations and two warp-level
-// carries; every lane then walks its own 32 positions with two counters,
-//   s(z) = +-min(z-a+1, e-z)^2   ([a,e) = the run of equal polarity around z),
-// and the 32x32 block is transposed through a padded shared-memory tile so rows leave as 128-byte coalesced stores.
-template <int WPL>   // words (of 32 positions) per lane: 1 for nz <= 1024, 2 for nz <= 2048
+// Binary pass along the contiguous z axis: s(z) = +-min(z-a+1, e-z)^2 with [a,e) the run of equal polarity around z
+// (squared distance to the nearest voxel of the other polarity on the line; SDF_INF if there is none).
+// A group of LPL lanes owns one line (nz <= 32*LPL), each lane one 32-position word: the lane loads its own 32
+// occupancy bytes (2 x 16 B, or byte-wise when unaligned), packs them into a bit word, run boundaries come from bit
+// operations plus two group-level carries (ballot + shuffle), every lane then walks its 32 positions with two
+// counters, and the warp's 32x32 block is transposed through a padded shared tile so rows leave as 128-byte stores.
+// carries (slab builds): per line {distance from z=0 / z=nz-1 to the nearest other-polarity voxel in the slabs below /
+// above}, FARB = none.
+__device__ __forceinline__ uint32_t pack_nonzero_bytes16(uint4 x)
+{
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t t = __vcmpne4(xs[q], 0u) & 0x01010101u;          // 1 per non-zero byte
+        bits |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * q);
+    }
+    return bits;
+}
+
+template <int LPL, int WPL>   // lanes per line; words per lane (WPL = 2 only with LPL = 32, for nz in (1024, 2048])
 __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ out,
                                                        int nz, int64_t nlines, const int2* __restrict__ carries)
 {
+    static_assert(WPL == 1 || LPL == 32, "two words per lane only for full-warp lines");
     __shared__ int32_t tile_all[8][32 * 33];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t line = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (line >= nlines) return;
-    int32_t* tile = tile_all[wib];
-    const uint8_t* mp = mask + line * nz;
-    int32_t* op = out + line * nz;
-    const int nw = (nz + 31) >> 5;
+    constexpr int LNW = 32 / LPL;               // lines per warp
     constexpr int FARB = 40000;                 // "no zero site on this side"
-    // slab builds: distance from this line's first / last voxel to the nearest voxel of the other polarity in the
-    // slabs below / above (FARB if none); whole-grid builds: nothing beyond the faces
-    const int2 cy = carries ? __ldg(carries + line) : make_int2(FARB, FARB);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = lane & (LPL - 1);             // word index inside the line (first block)
+    const int gbase = lane - g;                 // first lane of this line's group
+    const uint32_t gmask = (LPL == 32) ? 0xffffffffu : (((1u << LPL) - 1u) << gbase);
+    const int64_t line = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * LNW + (lane / LPL);
+    const bool line_ok = line < nlines;
+    int32_t* tile = tile_all[wib];
+    const uint8_t* mp = mask + (line_ok ? line : 0) * nz;
+    const int2 cy = (carries && line_ok) ? __ldg(carries + line) : make_int2(FARB, FARB);
+    const bool vec16 = ((nz & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);   // warp-uniform
+
     uint32_t P[WPL], PC[WPL];
     int a_in[WPL], e_in[WPL];
-    const bool vec16 = ((nz & 15) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);   // warp-uniform
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-        uint32_t mine = 0;
-        if (vec16) {
-            // two 16-byte loads per lane cover 1024 positions; 16 occupancy bits per load, regrouped by shuffles
-            uint32_t half[2];
-#pragma unroll
-            for (int hs = 0; hs < 2; ++hs) {
-                const int byte0 = (k * 2 + hs) * 512 + lane * 16;
-                uint32_t hbits = 0;
-                if (byte0 < nz) {
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(mp + byte0));
-                    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t t = __vcmpne4(xs[q], 0u) & 0x01010101u;      // 1 per non-zero byte
-                        hbits |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * q);
-                    }
-                }
-                half[hs] = hbits;
-            }
-            const int src = (lane & 15) * 2;
-            const uint32_t a0 = __shfl_sync(0xffffffffu, half[0], src), b0 = __shfl_sync(0xffffffffu, half[0], src + 1);
-            const uint32_t a1 = __shfl_sync(0xffffffffu, half[1], src), b1 = __shfl_sync(0xffffffffu, half[1], src + 1);
-            mine = (lane < 16) ? (a0 | (b0 << 16)) : (a1 | (b1 << 16));
-        } else {
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const int w = k * 32 + i;
-                if (w < nw) {                       // warp-uniform
-                    const int z = w * 32 + lane;
-                    const bool f = (z < nz) ? (__ldg(mp + z) != 0) : false;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, f);
-                    if (lane == i) mine = bal;
-                }
+        const int z0 = (k * 32 + g) * 32;
+        uint32_t p = 0;
+        if (line_ok && z0 < nz) {
+            if (vec16) {
+                p = pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0)));
+                if (z0 + 16 < nz) p |= pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0 + 16))) << 16;
+            } else {
+                for (int j = 0; j < 32 && z0 + j < nz; ++j) p |= (uint32_t)(__ldg(mp + z0 + j) != 0) << j;
             }
         }
-        P[k] = mine;
+        P[k] = p;
     }
     // run-start bits: polarity differs from the previous position
-    uint32_t carry_top = P[0] & 1u;             // position 0 never starts a "new" run
+    uint32_t carry_top = __shfl_sync(0xffffffffu, P[0] & 1u, gbase);   // position 0 never starts a "new" run
     int last_run_start = -1;                    // carried across the WPL blocks
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-        const int w = k * 32 + lane;
+        const int w = k * 32 + g;
         uint32_t prevtop = __shfl_up_sync(0xffffffffu, P[k] >> 31, 1);
-        if (lane == 0) prevtop = carry_top;
-        carry_top = __shfl_sync(0xffffffffu, P[k] >> 31, 31);
+        if (g == 0) prevtop = carry_top;
+        carry_top = __shfl_sync(0xffffffffu, P[k] >> 31, gbase + LPL - 1);
         uint32_t pc = P[k] ^ ((P[k] << 1) | prevtop);
         const int valid = nz - w * 32;
         if (valid < 32) pc &= (valid > 0) ? ((1u << valid) - 1u) : 0u;
         PC[k] = pc;
-        const uint32_t bal = __ballot_sync(0xffffffffu, pc != 0);
+        const uint32_t bal = __ballot_sync(0xffffffffu, pc != 0) & gmask;
         const int myhi = pc ? (w * 32 + 31 - __clz((int)pc)) : -1;
         const uint32_t lower = bal & ((1u << lane) - 1u);
         const int src = lower ? (31 - __clz((int)lower)) : 0;
         const int from = __shfl_sync(0xffffffffu, myhi, src);
         a_in[k] = lower ? from : last_run_start;
-        const int blk_last = bal ? __shfl_sync(0xffffffffu, myhi, 31 - __clz((int)bal)) : -1;
-        if (blk_last >= 0) last_run_start = blk_last;
+        const int blk_last = __shfl_sync(0xffffffffu, myhi, bal ? (31 - __clz((int)bal)) : 0);
+        if (bal) last_run_start = blk_last;
     }
     int next_run_start = nz;                    // carried backwards across the blocks
 #pragma unroll
     for (int k = WPL - 1; k >= 0; --k) {
-        const int w = k * 32 + lane;
+        const int w = k * 32 + g;
         const uint32_t pc = PC[k];
-        const uint32_t bal = __ballot_sync(0xffffffffu, pc != 0);
+        const uint32_t bal = __ballot_sync(0xffffffffu, pc != 0) & gmask;
         const int mylo = pc ? (w * 32 + __ffs((int)pc) - 1) : nz;
         const uint32_t upper = (lane < 31) ? (bal & ~((2u << lane) - 1u)) : 0u;
         const int src = upper ? (__ffs((int)upper) - 1) : 0;
         const int from = __shfl_sync(0xffffffffu, mylo, src);
         e_in[k] = upper ? from : next_run_start;
-        const int blk_first = bal ? __shfl_sync(0xffffffffu, mylo, __ffs((int)bal) - 1) : nz;
-        if (blk_first < nz) next_run_start = blk_first;
+        const int blk_first = __shfl_sync(0xffffffffu, mylo, bal ? (__ffs((int)bal) - 1) : 0);
+        if (bal) next_run_start = blk_first;
     }
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-        if (k * 32 < nw) {                      // warp-uniform
-            const int z0 = (k * 32 + lane) * 32;
-            const uint32_t p = P[k], pc = PC[k];
-            int dl = (a_in[k] >= 1) ? (z0 - a_in[k] + 1) : (cy.x < FARB ? z0 + cy.x : FARB);       // z - a + 1
-            int e = (pc & ~1u) ? (z0 + __ffs((int)(pc & ~1u)) - 1) : e_in[k];     // first run start after z0
-            int dr = (e < nz) ? (e - z0) : (cy.y < FARB ? nz - 1 - z0 + cy.y : FARB);              // e - z
+        const int z0 = (k * 32 + g) * 32;
+        const uint32_t p = P[k], pc = PC[k];
+        int dl = (a_in[k] >= 1) ? (z0 - a_in[k] + 1) : (cy.x < FARB ? z0 + cy.x : FARB);       // z - a + 1
+        int e = (pc & ~1u) ? (z0 + __ffs((int)(pc & ~1u)) - 1) : e_in[k];                      // first run start after z0
+        int dr = (e < nz) ? (e - z0) : (cy.y < FARB ? nz - 1 - z0 + cy.y : FARB);              // e - z
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if ((pc >> j) & 1u) {           // a run starts here
-                    dl = 1;
-                    const uint32_t rest = (j < 31) ? (pc >> (j + 1)) : 0u;
-                    e = rest ? (z0 + j + __ffs((int)rest)) : e_in[k];
-                    dr = (e < nz) ? (e - z0 - j) : (cy.y < FARB ? nz - 1 - z0 - j + cy.y : FARB);
-                }
-                const int d = dl < dr ? dl : dr;
-                const int32_t v = (d >= FARB) ? SDF_INF : d * d;
-                tile[lane * 33 + j] = ((p >> j) & 1u) ? -v : v;
-                ++dl; --dr;
+        for (int j = 0; j < 32; ++j) {
+            if ((pc >> j) & 1u) {               // a run starts here
+                dl = 1;
+                const uint32_t rest = (j < 31) ? (pc >> (j + 1)) : 0u;
+                e = rest ? (z0 + j + __ffs((int)rest)) : e_in[k];
+                dr = (e < nz) ? (e - z0 - j) : (cy.y < FARB ? nz - 1 - z0 - j + cy.y : FARB);
             }
-            __syncwarp();
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const int z = (k * 32 + r) * 32 + lane;
-                if (z < nz) op[z] = tile[r * 33 + lane];
-            }
-            __syncwarp();
+            const int d = dl < dr ? dl : dr;
+            const int32_t v = (d >= FARB) ? SDF_INF : d * d;
+            tile[lane * 33 + j] = ((p >> j) & 1u) ? -v : v;
+            ++dl; --dr;
         }
+        __syncwarp();
+        // row r of the tile = word (r % LPL) of the warp's line (r / LPL)
+        const int64_t line0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wib) * LNW;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const int64_t ln = line0 + r / LPL;
+            const int z = (k * 32 + (r & (LPL - 1))) * 32 + lane;
+            if (ln < nlines && z < nz) out[ln * nz + z] = tile[r * 33 + lane];
+        }
+        __syncwarp();
     }
 }
 
@@ -371,16 +364,27 @@ cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st)
     return cudaGetLastError();
 }
 
+template <int LPL, int WPL>
+static cudaError_t launch_binary_z_cfg(const uint8_t* m, int32_t* out, int nz, int64_t nlines, const int2* cy, cudaStream_t st)
+{
+    const int wpb = 8;
+    const int64_t lines_per_block = (int64_t)wpb * (32 / LPL);
+    binary_z_kernel<LPL, WPL><<<(unsigned)((nlines + lines_per_block - 1) / lines_per_block), wpb * 32, 0, st>>>(m, out, nz, nlines, cy);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, const void* d_carries,
                             cudaStream_t st)
 {
-    if (nz > 2048) return cudaErrorInvalidValue;
-    const int wpb = 8;
-    const unsigned blocks = (unsigned)((nlines + wpb - 1) / wpb);
     const int2* cy = reinterpret_cast<const int2*>(d_carries);
-    if (nz <= 1024) binary_z_kernel<1><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines, cy);
-    else binary_z_kernel<2><<<blocks, wpb * 32, 0, st>>>(d_mask, d_out, nz, nlines, cy);
-    return cudaGetLastError();
+    if (nz <= 32) return launch_binary_z_cfg<1, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 64) return launch_binary_z_cfg<2, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 128) return launch_binary_z_cfg<4, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 256) return launch_binary_z_cfg<8, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 512) return launch_binary_z_cfg<16, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 1024) return launch_binary_z_cfg<32, 1>(d_mask, d_out, nz, nlines, cy, st);
+    if (nz <= 2048) return launch_binary_z_cfg<32, 2>(d_mask, d_out, nz, nlines, cy, st);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_slab_summary(const uint8_t* d_mask, int nz, int64_t nlines, uint32_t* d_summary, cudaStream_t st)
