@@ -9,7 +9,7 @@
  *          = classify (:219-240) + 2 x BuildDistanceField (:95-207, called at :242-243) + combine (:246-268)
  * and, from Python, through pysdf_tools.CollisionMapGrid.ExtractSignedDistanceField (src/sdf_tools/bindings.cpp:81).
  * Each entry point below names the reference code it stands in for.  The C++ face that mirrors the reference
- * signatures (include/sdf_tools_b200/*.hpp) and the Python face (sdf_tools_b200.pysdf_tools) are thin callers
+ * signatures (include/sdf_tools/ headers) and the Python face (sdf_tools_b200.pysdf_tools) are thin callers
  * of this ABI; INTEGRATION.md shows the binding a reference maintainer would add.
  *
  * Conventions

@@ -45,6 +45,33 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def pybind_path() -> str:
+    import sysconfig
+    return os.path.join(_HERE, "pysdf_tools" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pybind(force: bool = False) -> str:
+    """Compile the pybind11 module `pysdf_tools` (C++ face + Python face of the reference API) with g++."""
+    import sysconfig
+    import pybind11
+    out = pybind_path()
+    src = os.path.join(CSRC, "pybind_module.cpp")
+    inc = os.path.join(os.path.dirname(_HERE), "include")
+    deps = [src, LIB_PATH] + [os.path.join(inc, "sdf_tools", f) for f in ("sdf.hpp", "sdf_generation.hpp", "collision_map.hpp")] \
+        + [os.path.join(inc, "arc_utilities", "voxel_grid.hpp"), os.path.join(inc, "sdf_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cxx = "g++" if os.path.exists("/usr/bin/g++") else (os.environ.get("CXX") or "g++")
+    cmd = [cxx if cxx != "g++" else "/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-I", inc, "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], src, "-o", out + ".tmp",
+           "-L", LIB_DIR, "-lsdf_b200", "-Wl,-rpath,$ORIGIN/lib"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ (pybind module) failed:\n" + res.stdout + res.stderr)
+    os.replace(out + ".tmp", out)
+    return out
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

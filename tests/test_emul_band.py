@@ -1,0 +1,101 @@
+"""CPU tests of the kernel ALGORITHM: the phase functions of sdf_tools_b200/csrc/band_hull.cuh (the same source the
+CUDA kernel compiles) run on the host as loops over the (line, band) threads of a tile (tests/emul/emul_band.cpp),
+in natural and shuffled thread order, against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sdf_tools_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emul", "emul_band.cpp")
+LIB = os.path.join(HERE, "emul", "_build", "libemul_band.so")
+CFGS = [(3, 4), (4, 4), (5, 4), (6, 4), (5, 16), (5, 32), (6, 8), (4, 32), (3, 32)]     # (log2 band, lines per CTA)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    hdr = os.path.join(HERE, "..", "sdf_tools_b200", "csrc", "band_hull.cuh")
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                               "-o", LIB, SRC])
+    L = C.CDLL(LIB)
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+    L.emul_band_signed_d2.argtypes = [u8p, C.c_int64, C.c_int64, C.c_int64, i32p, C.c_int, C.c_int, C.c_int, C.c_uint64]
+    L.emul_band_pass.argtypes = [i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64]
+    return L
+
+
+def line_oracle(s):
+    """out(p) = min over q of (p-q)^2 + (|s(q)| if same polarity else 0): the definition, O(n^2)."""
+    n = len(s)
+    h = np.abs(s.astype(np.int64)); pol = s < 0; q = np.arange(n)
+    out = np.empty(n, np.int64)
+    for p in range(n):
+        same = pol == pol[p]
+        cost = (q - p) ** 2 + np.where(same, h, 0)
+        cost = np.where(same & (h >= O.INF), 2 ** 40, cost)
+        out[p] = min(cost.min(), O.INF)
+    return np.where(pol, -out, out).astype(np.int32)
+
+
+def test_full_transform_random_grids(lib):
+    rng = np.random.default_rng(0)
+    for trial in range(45):
+        shape = tuple(int(v) for v in rng.integers(1, 70, size=3))
+        p = rng.choice([0.001, 0.01, 0.05, 0.3, 0.5, 0.9, 0.99])
+        m = (rng.random(shape) < p).astype(np.uint8)
+        logb, lpc = CFGS[trial % len(CFGS)]
+        got = np.empty(shape, np.int32)
+        assert lib.emul_band_signed_d2(m, *shape, got, logb, lpc, trial % 2, trial) == 0
+        assert np.array_equal(got, O.signed_d2(m)), (shape, p, logb, lpc)
+
+
+def test_line_passes_adversarial(lib):
+    rng = np.random.default_rng(7)
+    INF = O.INF
+    for trial in range(40):
+        n = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 100, 255, 256, 511, 513, 1000, 1024, 1025, 2047, 2048]))
+        ncols = int(rng.integers(1, 5))
+        lines = []
+        for _ in range(ncols):
+            kind = rng.integers(0, 5)
+            if kind == 0: h = rng.integers(1, 50, n)
+            elif kind == 1: h = rng.integers(1, 3 * n * n + 2, n)
+            elif kind == 2: h = np.abs(np.arange(n) - rng.integers(0, n)) ** 2 + rng.integers(1, 20, n)
+            elif kind == 3:
+                h = np.full(n, INF); k = rng.integers(0, n, max(1, n // 50)); h[k] = rng.integers(1, 10000, len(k))
+            else: h = np.where(rng.random(n) < 0.5, INF, rng.integers(1, 1000, n))
+            h = np.minimum(h, INF)
+            pp = rng.choice([0.0, 0.001, 0.02, 0.3, 0.5, 1.0])
+            pol = np.zeros(n, bool)
+            if pp > 0:
+                if rng.random() < 0.5:
+                    pol = rng.random(n) < pp
+                else:
+                    x = 0
+                    while x < n:
+                        L = int(rng.integers(1, max(2, n // 4))); pol[x:x + L] = rng.random() < pp; x += L
+            lines.append(np.where(pol, -h, h).astype(np.int32))
+        g = np.ascontiguousarray(np.stack(lines, axis=1))
+        want = np.stack([line_oracle(l) for l in lines], axis=1)
+        for logb, lpc in [(3, 4), (5, 16), (5, 32), (6, 8)]:
+            if n > (64 << logb):
+                continue
+            got = g.copy()
+            assert lib.emul_band_pass(got, n, ncols, ncols, logb, lpc, trial % 2, trial) == 0
+            assert np.array_equal(got, want), (n, logb, lpc)
+
+
+@pytest.mark.parametrize("name,shape", [("c2", (48, 48, 48)), ("c3", (64, 64, 64)), ("c5", (64, 64, 64))])
+def test_structured_configs(lib, name, shape):
+    m = synth.make_mask(name, shape)
+    got = np.empty(shape, np.int32)
+    assert lib.emul_band_signed_d2(m, *shape, got, 5, 16, 1, 3) == 0
+    assert np.array_equal(got, O.signed_d2(m))

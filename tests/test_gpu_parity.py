@@ -158,3 +158,14 @@ def test_slab_builds_on_one_gpu(ctx):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"slab build differs ({mask.shape}, {nr} slabs)"
         mx, mn = ctx.extrema_from_raw(max(a for a, _ in raws), max(b for _, b in raws), 0.05)
         assert (mx, mn) == (wmx, wmn)
+
+
+@pytest.mark.parametrize("name", __import__("golden_cases").NAMES)
+def test_against_golden_reference_output(ctx, name):
+    """The CUDA path vs REAL reference output committed in tests/golden (P0/P2/P3/P4)."""
+    import golden_cases as G
+    mask, res, ref, _ = G.load(name)
+    got, ext = ctx.build_from_mask(mask, res)
+    n_differ, max_rel = G.check_against_reference(name, got, ext)
+    if name in ("single_cell", "c1_64"):
+        assert n_differ == 0
