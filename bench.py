@@ -32,6 +32,15 @@ ALGO_BYTES_PER_VOXEL = 21.0          # 1+4 (pass 1) + 4+4 
 PASS_BYTES = {"pass1_z_ms": 5.0, "pass2_y_ms": 8.0, "pass3_x_ms": 8.0}
 
 
+def ncu_traffic(pass_key: str, nvox: int):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture (same grid only)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[pass_key]
+        return float(d["dram_bytes_per_launch"]) if nvox == 1024 ** 3 else None
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -165,7 +174,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-edge", type=int, default=160, help="edge of the CPU-baseline crop")
+    ap.add_argument("--cpu-edge", type=int, default=320, help="edge of the CPU-baseline crop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -238,7 +247,8 @@ def main():
     whole_gbs = ALGO_BYTES_PER_VOXEL * nvox / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": {"pass1_z_ms": "binary_z_kernel", "pass2_y_ms": "band_strided_kernel (y)",
                                            "pass3_x_ms": "band_strided_kernel (x, final)"}[dom],
-                "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None,
+                "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
+                "traffic": ncu_traffic(dom, nvox), "algorithmic_bytes_per_launch": PASS_BYTES[dom] * nvox,
                 "peak_source": peak_src, "algorithmic_bytes_per_voxel": PASS_BYTES[dom],
                 "kernel_ms": means[dom],
                 "whole_build": {"achieved": whole_gbs, "frac": whole_gbs / peak,
@@ -279,7 +289,7 @@ def main():
     out = {
         "metric": "Mvox/s SDF build", "value": value, "unit": "Mvox/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "int32 d2 -> f32 (f64 sqrt)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "int32 d2 -> f32 (exact f64 sqrt table)", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['desc']}", "grid": [nx, ny, nz], "resolution": res,
                    "fill": fill, "l2": "inputs (1 B + 4 B per voxel) larger than L2; no flush needed",
                    "extrema": [mx, mn]},
