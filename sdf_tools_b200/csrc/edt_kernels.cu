@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) sqrt_lut_kernel(float* __restrict__ lut, 
 }
 
 template <int LOGB, int LPC, bool FINAL>
-__global__ void __launch_bounds__(32 * LPC, (LPC == 16 && LOGB == 5) ? 3 : 1) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
+__global__ void __launch_bounds__(32 * LPC, (LOGB == 5 && LPC == 16) ? 3 : ((LOGB == 5 && LPC == 8) ? 6 : 1)) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
                                                                  int64_t line_stride, int64_t ncols,
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
