@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(256) sqrt_lut_kernel(float* __restrict__ lut, 
     if (m < n) lut[m] = (float)(sqrt((double)m) * res);
 }
 
-template <int LOGB, int LPC, bool FINAL>
-__global__ void __launch_bounds__(32 * LPC, (LOGB == 5 && LPC == 16) ? 3 : ((LOGB == 5 && LPC == 8) ? 6 : 1)) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
+template <int LOGB, int LPC, int NBMAX, bool FINAL>   // NBMAX = most bands per line this instance is launched with
+__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
                                                                  int64_t line_stride, int64_t ncols,
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
@@ -402,15 +402,16 @@ cudaError_t launch_slab_carry(const uint32_t* d_all, const int* d_widths, int nr
     return cudaGetLastError();
 }
 
-template <int LOGB, int LPC, bool FINAL>
+template <int LOGB, int LPC, int NBMAX, bool FINAL>
 static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
                                    int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
                                    cudaStream_t st)
 {
     constexpr int B = 1 << LOGB;
     const int nb = (n + B - 1) / B;
+    if (nb > NBMAX) return cudaErrorInvalidValue;
     const size_t smem = (size_t)nb * B * LPC * 4 + (size_t)nb * LPC * 4 + (size_t)nb * LPC * 8;
-    auto kern = band_strided_kernel<LOGB, LPC, FINAL>;
+    auto kern = band_strided_kernel<LOGB, LPC, NBMAX, FINAL>;
     if (smem > 48 * 1024) {   // per-device attribute; cheap enough to set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -420,20 +421,16 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
     return cudaGetLastError();
 }
 
+// Tile shapes: bands of 32 rows everywhere; lines per CTA chosen so a CTA has <= 512 threads and ~64 KB of stacks
+// (3 CTAs per SM): n <= 256 -> 32 lines x <= 8 bands, n <= 1024 -> 16 lines x <= 32 bands, n <= 2048 -> 8 lines x <= 64 bands.
 template <bool FINAL>
 static cudaError_t launch_band_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
-                                   cudaStream_t st)
+                                 cudaStream_t st)
 {
-    if (n <= 256) return launch_band_cfg<5, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
-    if (n <= 1024) {
-        static int lpc = -1;                      // tuning knob (SDF_B200_LPC=8|16|32), default 16
-        if (lpc < 0) { const char* e = getenv("SDF_B200_LPC"); lpc = e ? atoi(e) : 16; }
-        if (lpc == 8) return launch_band_cfg<5, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
-        if (lpc == 32) return launch_band_cfg<5, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
-        return launch_band_cfg<5, 16, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
-    }
-    if (n <= 2048) return launch_band_cfg<6, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    if (n <= 256) return launch_band_cfg<5, 32, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    if (n <= 1024) return launch_band_cfg<5, 16, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    if (n <= 2048) return launch_band_cfg<5, 8, 64, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     return cudaErrorInvalidValue;
 }
 

@@ -58,7 +58,7 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
 static int dispatch(int32_t* g, int n, int64_t ls, int64_t ncols, int shuffle, int logb, int lpc)
 {
 #define CASE(LB, LP) if (logb == LB && lpc == LP) { pass_strided<LB, LP>(g, n, ls, ncols, shuffle); return 0; }
-    CASE(3, 4) CASE(4, 4) CASE(5, 4) CASE(6, 4) CASE(5, 16) CASE(5, 32) CASE(6, 8) CASE(4, 32) CASE(3, 32)
+    CASE(3, 4) CASE(4, 4) CASE(5, 4) CASE(6, 4) CASE(5, 16) CASE(5, 32) CASE(5, 8) CASE(6, 8) CASE(4, 32) CASE(3, 32)
 #undef CASE
     return -1;
 }

@@ -85,7 +85,7 @@ def test_line_passes_adversarial(lib):
             lines.append(np.where(pol, -h, h).astype(np.int32))
         g = np.ascontiguousarray(np.stack(lines, axis=1))
         want = np.stack([line_oracle(l) for l in lines], axis=1)
-        for logb, lpc in [(3, 4), (5, 16), (5, 32), (6, 8)]:
+        for logb, lpc in [(3, 4), (5, 16), (5, 32), (5, 8), (6, 8)]:
             if n > (64 << logb):
                 continue
             got = g.copy()
