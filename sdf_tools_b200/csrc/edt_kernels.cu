@@ -15,9 +15,11 @@
 #include "edt_kernels.cuh"
 #include "band_hull.cuh"
 
+#include <cuda.h>            // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched at run time (no -lcuda)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 
 namespace sdfb200 {
@@ -255,7 +257,8 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
                                                                  int64_t line_stride, int64_t ncols,
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
-                                                                 const float* __restrict__ lut, int lut_n)
+                                                                 const float* __restrict__ lut, int lut_n,
+                                                                 const __grid_constant__ CUtensorMap tmap, int use_tma)
 {
     using BH = BandHull<LOGB, LPC>;
     // optional phase clocks (diagnostics): thread 0 of the first 1024 CTAs stores clock64() at phase boundaries
@@ -265,7 +268,8 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
     const bool dbg_on = dbg != nullptr && threadIdx.x == 0 && (dbg_lin % dbg_stride) == 0 && dbg_cta < 1024;
     if (dbg_on) dbg[dbg_cta * 8 + 0] = clock64();
     constexpr int B = BH::B;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long tma_bar;
     BandTile T;
     {
         uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -284,7 +288,41 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
     while ((1 << nlevels) < nb) ++nlevels;
 
     typename BH::pcw_t Pw, PCw;
-    {
+    if (use_tma) {
+        // Tile staging by TMA: one 3-D tensor-map box (LPC columns x 32 rows x 1) per band lands directly in the band's
+        // stack slots (the slot layout [row][line] IS the dense box layout); rows / columns outside the grid arrive as
+        // zeros and are never read.  One thread arms an mbarrier with the byte count and issues the copies; everybody
+        // waits on the barrier's phase.
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)nb * B * LPC * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            const int c0 = (int)(blockIdx.x * LPC), o = (int)blockIdx.y;
+            for (int bb = 0; bb < nb; ++bb) {
+                const uint32_t dstp = T.S + (uint32_t)bb * (B * LPC * 4u);
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             :: "r"(dstp), "l"(&tmap), "r"(c0), "r"(bb * B), "r"(o), "r"(bar) : "memory");
+            }
+        }
+        uint32_t done = 0;
+        int spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+            if (!done && ++spins > (1 << 22)) __trap();       // never hang the device on a mis-programmed copy
+        }
+        // polarity of the position just before the band, read from the staged tile before any stack overwrites it
+        const int qp = b > 0 ? base - 1 : 0;
+        const bool prevpol = col_ok ? ((int32_t)bh_ld32(T.S + 4u * (uint32_t)(qp * LPC + c)) < 0) : false;
+        if (dbg_on) dbg[dbg_cta * 8 + 1] = clock64();
+        __syncthreads();
+        BH::build(T, c, b, col_ok ? n : 0, prevpol, Pw, PCw);
+    } else {
         // stage the band's values into its own stack slots (the hull is then built in place)
         const bh_addr_t slot0 = T.S + 4u * (uint32_t)BH::sidx(b, 0, c);
         constexpr int U = 8;
@@ -402,6 +440,26 @@ cudaError_t launch_slab_carry(const uint32_t* d_all, const int* d_widths, int nr
     return cudaGetLastError();
 }
 
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_fn tensor_map_encoder()
+{
+    static tensor_map_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tensor_map_encode_fn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
 template <int LOGB, int LPC, int NBMAX, bool FINAL>
 static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
                                    int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
@@ -417,7 +475,25 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
         if (e != cudaSuccess) return e;
     }
     dim3 grid((unsigned)((ncols + LPC - 1) / LPC), (unsigned)nouter);
-    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n);
+    // 3-D tensor map of the pass's view of the field: (columns, rows along the axis, outer blocks), box = LPC x B x 1.
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int use_tma = 0;
+    static int tma_knob = -1;                         // SDF_B200_TMA=0 forces the LDG staging path
+    if (tma_knob < 0) { const char* e = getenv("SDF_B200_TMA"); tma_knob = (e && e[0] == '0') ? 0 : 1; }
+    const int64_t ostride = nouter > 1 ? outer_stride : line_stride * (int64_t)n;
+    if (tma_knob && tensor_map_encoder() && (line_stride % 4) == 0 && (ostride % 4) == 0 &&
+        (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)n, (cuuint64_t)nouter};
+        const cuuint64_t gstr[2] = {(cuuint64_t)line_stride * 4u, (cuuint64_t)ostride * 4u};
+        const cuuint32_t box[3] = {(cuuint32_t)LPC, (cuuint32_t)B, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, g, gdim, gstr, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
+    }
+    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, use_tma);
     return cudaGetLastError();
 }
 
