@@ -67,6 +67,12 @@ def run_multi(args, world: int, rank: int, local_rank: int):
         for k in per_pass:
             per_pass[k].append(tm[k])
     clocks = sampler.stop() if sampler else None
+    # per-rank kernel time (sum of the three passes): shows the data-dependent load imbalance between slabs
+    mine = torch.tensor([float(np.mean([sum(per_pass[k][j] for k in per_pass) for j in range(len(per_pass["pass1_z_ms"]))]))],
+                        dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    per_rank_ms = [round(float(t.item()), 4) for t in allr]
     mx, mn = sb.extrema(res)
     launches = (ctx.last_launches() + 1) * args.steps           # + the slab summary kernel
 
@@ -135,7 +141,7 @@ def run_multi(args, world: int, rank: int, local_rank: int):
                          "kernel_ms": means[dom],
                          "whole_build": {"achieved": whole_gbs, "peak": peak * world, "frac": whole_gbs / (peak * world),
                                          "algorithmic_bytes_per_voxel": ALGO_BYTES_PER_VOXEL},
-                         "per_pass_ms": means},
+                         "per_pass_ms": means, "per_rank_kernel_ms": per_rank_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(out))

@@ -38,7 +38,7 @@ extern "C" {
 #define SDF_B200_ERR_UNSUPPORTED (-3) /* an axis longer than SDF_B200_MAX_AXIS                       */
 #define SDF_B200_ERR_NOMEM (-4)       /* device or pinned-host allocation failed                     */
 
-#define SDF_B200_MAX_AXIS 2048        /* 32 lanes x 64-bit hull masks per line                       */
+#define SDF_B200_MAX_AXIS 2048        /* 64 bands of 32 rows per line in the envelope kernel        */
 #define SDF_B200_INF 0x40000000       /* |signed d2| sentinel: no voxel of the other polarity exists */
 
 typedef struct sdf_b200_ctx sdf_b200_ctx;

@@ -104,7 +104,6 @@ static long long bh_counters[8];
 #else
 #define BH_TICK(x) ((void)0)
 #endif
-constexpr int BH_NONE = -1;
 constexpr int BH_BIG = 0x7fff;          // "no run boundary after": larger than any position
 
 // Shared-memory arrays of one tile.  On the GPU the handles are 32-bit shared-window byte addresses accessed

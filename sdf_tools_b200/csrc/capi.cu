@@ -21,6 +21,8 @@ struct sdf_b200_ctx {
     double lut_res = -1.0;
     long long* d_dbg = nullptr;        // optional phase clocks of the band kernels: [pass 2|3][1024 CTAs][8]
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;  // host entry points: H2D / D2H chunks overlap the kernels of the other chunks
+    cudaEvent_t chunk_ev[17] = {};       // [0..7] upload chunks, [8..15] download chunks, [16] stream hand-over
     bool timed = false;
     int launches = 0;
     void* d_in = nullptr;  size_t in_bytes = 0;     // staging for the host entry points
@@ -95,6 +97,8 @@ int sdf_b200_create(sdf_b200_ctx** out, int device)
         return SDF_B200_ERR_CUDA;
     }
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 17; ++i) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return SDF_B200_OK;
@@ -106,6 +110,8 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 17; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->d_ext) cudaFree(ctx->d_ext);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
     if (ctx->d_lut) cudaFree(ctx->d_lut);
@@ -331,9 +337,76 @@ static int build_host_common(sdf_b200_ctx* ctx, const void* h_in, size_t in_byte
     return sdf_b200_get_extrema(ctx, out_max, out_min);
 }
 
+// Large grids from host masks: the same three passes, software-pipelined against the PCIe copies.
+//   x-chunks :  H2D(mask chunk i) on the copy stream  ->  K1 + K2 of chunk i on the compute stream (both are local to
+//               an x range), so the upload of chunk i+1 hides behind the kernels of chunk i;
+//   column-chunks of the final x pass (a y range, all z): each finishes every x of its columns, so its result leaves
+//               with one strided D2H (nx rows of ychunk*nz floats) while the next chunk is still computing.
+// Result and extrema are identical to the unpipelined path: chunks only partition independent lines.
+static int build_host_pipelined(sdf_b200_ctx* ctx, const uint8_t* h_mask, int64_t nx, int64_t ny, int64_t nz, double res,
+                                float* out_sdf, double* out_max, double* out_min)
+{
+    constexpr int NCH = 8;
+    constexpr int LUT_N = 1 << 20;
+    const int64_t N = nx * ny * nz, plane = ny * nz;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)N))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    uint8_t* d_mask = (uint8_t*)ctx->d_mask;
+    int32_t* d_field = (int32_t*)ctx->d_out;
+    ctx->launches = 0;
+    ctx->timed = false;
+    CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
+    if (ctx->d_lut == nullptr || ctx->lut_res != res) {
+        if (!ctx->d_lut) CK(cudaMalloc(&ctx->d_lut, (size_t)LUT_N * sizeof(float)), "cudaMalloc(lut)");
+        CK(sdfb200::launch_sqrt_lut(ctx->d_lut, LUT_N, res, st), "launch sqrt_lut");
+        ctx->lut_res = res;
+        ctx->launches++;
+    }
+    CK(cudaEventRecord(ctx->chunk_ev[16], st), "event");          // copies must not overtake earlier work on `st`
+    CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[16], 0), "wait");
+    for (int i = 0; i < NCH; ++i) {                                 // ---- upload + z / y passes, chunked along x
+        const int64_t x0 = nx * i / NCH, x1 = nx * (i + 1) / NCH;
+        if (x1 == x0) continue;
+        const int64_t off = x0 * plane, cnt = (x1 - x0) * plane;
+        CK(cudaMemcpyAsync(d_mask + off, h_mask + off, (size_t)cnt, cudaMemcpyHostToDevice, cs), "H2D mask chunk");
+        CK(cudaEventRecord(ctx->chunk_ev[i], cs), "event");
+        CK(cudaStreamWaitEvent(st, ctx->chunk_ev[i], 0), "wait");
+        CK(sdfb200::launch_binary_z(d_mask + off, d_field + off, (int)nz, (x1 - x0) * ny, nullptr, st), "launch binary_z");
+        ctx->launches++;
+        if (ny > 1) {
+            CK(sdfb200::launch_band_strided(d_field + off, (int)ny, nz, nz, x1 - x0, plane, false, res, ctx->d_ext, nullptr,
+                                            nullptr, 0, st), "launch band_strided(y)");
+            ctx->launches++;
+        }
+    }
+    for (int j = 0; j < NCH; ++j) {                                 // ---- final x pass + download, chunked along y
+        const int64_t y0 = ny * j / NCH, y1 = ny * (j + 1) / NCH;
+        if (y1 == y0) continue;
+        const int64_t col0 = y0 * nz, ncols = (y1 - y0) * nz;
+        CK(sdfb200::launch_band_strided(d_field + col0, (int)nx, plane, ncols, 1, 0, true, res, ctx->d_ext, nullptr,
+                                        ctx->d_lut, LUT_N, st), "launch band_strided(x)");
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->chunk_ev[8 + j], st), "event");
+        CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[8 + j], 0), "wait");
+        CK(cudaMemcpy2DAsync(out_sdf + col0, (size_t)plane * 4, d_field + col0, (size_t)plane * 4, (size_t)ncols * 4,
+                             (size_t)nx, cudaMemcpyDeviceToHost, cs), "D2H sdf chunk");
+    }
+    CK(cudaStreamSynchronize(cs), "sync copies");
+    ctx->built = true;
+    ctx->res = res;
+    return sdf_b200_get_extrema(ctx, out_max, out_min);
+}
+
 int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz,
                              double resolution, float* out_sdf, double* out_max, double* out_min)
 {
+    if (ctx && mask && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx >= 64 && ny >= 64 &&
+        nx * ny * nz >= ((int64_t)1 << 25)) {           // big enough for the copies to be worth overlapping
+        CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+        return build_host_pipelined(ctx, mask, nx, ny, nz, resolution, out_sdf, out_max, out_min);
+    }
     return build_host_common(ctx, mask, (size_t)(nx * ny * nz), false, 0, nx, ny, nz, resolution, out_sdf, out_max, out_min);
 }
 

@@ -169,3 +169,14 @@ def test_against_golden_reference_output(ctx, name):
     n_differ, max_rel = G.check_against_reference(name, got, ext)
     if name in ("single_cell", "c1_64"):
         assert n_differ == 0
+
+
+def test_pipelined_host_path(ctx):
+    """Grids >= 2^25 voxels from host masks take the chunked, copy-overlapped path (capi.cu build_host_pipelined):
+    same passes on x-chunks / column-chunks, so the result must stay bit-identical to the oracle."""
+    for mask, res in ((synth.make_mask("c3", (256, 256, 512)), 0.01), (synth.iid((300, 264, 430), 0.02, 17), 0.05)):
+        assert mask.size >= 1 << 25
+        want, wmx, wmn = O.build_sdf(mask, res)
+        got, (mx, mn) = ctx.build_from_mask(mask, res)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert (mx, mn) == (wmx, wmn)
