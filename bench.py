@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--cpu-edge", type=int, default=320, help="edge of the CPU-baseline crop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N > 1: gather the slabs on rank 0 and compare with the CPU oracle (small workloads)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

@@ -31,14 +31,14 @@ def run_multi(args, world: int, rank: int, local_rank: int):
 
     ctx = Context(local_rank)
     sb = SlabBuilder(ctx, (nx, ny, nz), rank, world)
-    mask_h = synth.make_mask(args.workload, zrange=(sb.z0, sb.z1))
-    nloc = mask_h.size
-    d_mask = torch.from_numpy(mask_h).cuda()
-    d_sdf = torch.empty((nx, ny, sb.nzl), dtype=torch.float32, device="cuda")
+    masks_h = [synth.make_mask(args.workload, zrange=r) for r in sb.local_ranges]   # this rank's slabs (cyclic deal)
+    nloc = sum(m.size for m in masks_h)
+    d_masks = [torch.from_numpy(m).cuda() for m in masks_h]
+    d_sdfs = sb.alloc_outputs()
     stream = torch.cuda.current_stream()
 
     def step():
-        sb.build(d_mask, res, d_sdf)
+        sb.build(d_masks, res, d_sdfs)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -61,11 +61,19 @@ def run_multi(args, world: int, rank: int, local_rank: int):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     per_pass = {k: [] for k in PASS_BYTES}
-    for _ in range(min(args.steps, 5)):
-        step()
-        tm = ctx.last_timing()
+    ctx.set_stream(stream.cuda_stream)
+    for _ in range(min(args.steps, 5)):                  # per-kernel times: build the rank's slabs one by one
+        acc = {k: 0.0 for k in per_pass}
+        sb.build(d_masks, res, d_sdfs)                   # (fills the gathered summaries)
+        for p_i, (m_, o_) in enumerate(zip(d_masks, d_sdfs)):
+            k_ = sb.slab_ids[p_i]
+            ctx.slab_build_device(m_.data_ptr(), nx, ny, sb.widths[k_], res, sb.all_summaries.data_ptr() if world > 1
+                                  else sb.summary.data_ptr(), sb.widths, k_, o_.data_ptr(), keep_extrema=(p_i > 0))
+            tm = ctx.last_timing()
+            for k in per_pass:
+                acc[k] += tm[k]
         for k in per_pass:
-            per_pass[k].append(tm[k])
+            per_pass[k].append(acc[k])
     clocks = sampler.stop() if sampler else None
     # per-rank kernel time (sum of the three passes): shows the data-dependent load imbalance between slabs
     mine = torch.tensor([float(np.mean([sum(per_pass[k][j] for k in per_pass) for j in range(len(per_pass["pass1_z_ms"]))]))],
@@ -74,7 +82,7 @@ def run_multi(args, world: int, rank: int, local_rank: int):
     dist.all_gather(allr, mine)
     per_rank_ms = [round(float(t.item()), 4) for t in allr]
     mx, mn = sb.extrema(res)
-    launches = (ctx.last_launches() + 1) * args.steps           # + the slab summary kernel
+    launches = (ctx.last_launches() + 1) * sb.parts * args.steps   # per slab: summary + carry + 3 passes
 
     # ------------------------------------------------------------------------------------------- end to end
     e2e = None
@@ -83,14 +91,21 @@ def run_multi(args, world: int, rank: int, local_rank: int):
         h_in, h_out = C.c_void_p(), C.c_void_p()
         assert lib.sdf_b200_host_alloc(C.byref(h_in), nloc) == 0
         assert lib.sdf_b200_host_alloc(C.byref(h_out), nloc * 4) == 0
-        pin_mask = torch.from_numpy(np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=mask_h.shape))
-        pin_out = torch.from_numpy(np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_float)), shape=mask_h.shape))
-        pin_mask.copy_(torch.from_numpy(mask_h))
+        flat_in = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(nloc,))
+        flat_out = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_float)), shape=(nloc,))
+        pin_masks, pin_outs, off = [], [], 0
+        for m in masks_h:                                         # pinned host views, one per local slab
+            pin_masks.append(torch.from_numpy(flat_in[off:off + m.size].reshape(m.shape)))
+            pin_outs.append(torch.from_numpy(flat_out[off:off + m.size].reshape(m.shape)))
+            pin_masks[-1].copy_(torch.from_numpy(m))
+            off += m.size
 
         def e2e_step():
-            d_mask.copy_(pin_mask, non_blocking=True)            # H2D of this rank's slab
-            sb.build(d_mask, res, d_sdf)
-            pin_out.copy_(d_sdf, non_blocking=True)               # D2H of this rank's slab
+            for dm, pm in zip(d_masks, pin_masks):
+                dm.copy_(pm, non_blocking=True)                   # H2D of this rank's slabs
+            sb.build(d_masks, res, d_sdfs)
+            for po, ds in zip(pin_outs, d_sdfs):
+                po.copy_(ds, non_blocking=True)                   # D2H of this rank's slabs
             torch.cuda.synchronize()
             return sb.extrema(res)
 
@@ -113,6 +128,20 @@ def run_multi(args, world: int, rank: int, local_rank: int):
         lib.sdf_b200_host_free(h_in)
         lib.sdf_b200_host_free(h_out)
 
+    verified = None
+    if args.verify:                                       # not timed: every rank's slabs against the CPU oracle
+        from oracle import oracle as O
+        step()
+        torch.cuda.synchronize()
+        full = synth.make_mask(args.workload)
+        want, wmx, wmn = O.build_sdf(full, res)
+        ok = all(np.array_equal(o.cpu().numpy().view(np.uint32), want[:, :, a:b_].view(np.uint32))
+                 for o, (a, b_) in zip(d_sdfs, sb.local_ranges)) and (mx, mn) == (wmx, wmn)
+        t = torch.tensor([int(ok)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        verified = bool(t.item())
+        assert verified, f"rank {rank}: slab build differs from the oracle"
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         value = nvox / ms_per_step / 1e3
@@ -131,8 +160,9 @@ def run_multi(args, world: int, rank: int, local_rank: int):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32 d2 -> f32 (exact f64 sqrt table)", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg['desc']}", "grid": [nx, ny, nz], "resolution": res,
-                       "sharding": f"z slabs {sb.widths}", "collective": "1 all-gather of 4 B per z line per build "
-                       f"({nx * ny * 4} B per rank) + all-reduce of 2 ints for the extrema",
+                       "sharding": f"{sb.nslabs} z slabs of {sb.widths[0]} planes dealt cyclically, {sb.parts} per rank",
+                       "collective": f"{sb.parts} all-gather(s) of 4 B per z line per build "
+                       f"({nx * ny * 4} B per rank each) + all-reduce of 2 ints for the extrema",
                        "l2": "per-rank inputs larger than L2; no flush needed", "extrema": [mx, mn]},
             "roofline": {"bound": "hbm", "kernel": {"pass1_z_ms": "binary_z_kernel", "pass2_y_ms": "band_strided_kernel (y)",
                                                     "pass3_x_ms": "band_strided_kernel (x, final)"}[dom],
@@ -142,7 +172,7 @@ def run_multi(args, world: int, rank: int, local_rank: int):
                          "whole_build": {"achieved": whole_gbs, "peak": peak * world, "frac": whole_gbs / (peak * world),
                                          "algorithmic_bytes_per_voxel": ALGO_BYTES_PER_VOXEL},
                          "per_pass_ms": means, "per_rank_kernel_ms": per_rank_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "verified_vs_oracle": verified,
         }
         print(json.dumps(out))
     dist.barrier()

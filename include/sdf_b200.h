@@ -93,6 +93,10 @@ int sdf_b200_pack_cells_device(sdf_b200_ctx* ctx, const void* d_cells, int64_t n
 int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz,
                               int32_t* d_out);
 
+/* Same with HOST buffers (synchronous): out = nx*ny*nz int32.  Backs the BuildDistanceField compatibility wrapper of
+ * include/sdf_tools/sdf_generation.hpp: with seeds as the FILLED voxels, max(out, 0) is distance_square (:95-207). */
+int sdf_b200_signed_d2_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz, int32_t* out);
+
 /* Slab builds: the grid is cut along z into `nranks` slabs, one context (GPU) each -------------------------- */
 /* No reference counterpart (the reference is single-process); this is how the one BuildDistanceField pass that
  * crosses the cut (the binary pass along z) gets its context.  Protocol per build, on every rank:
@@ -100,13 +104,15 @@ int sdf_b200_signed_d2_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t 
  *   2. all-gather the summaries over the ranks (NCCL / torch.distributed; layout [rank][nx*ny])
  *   3. sdf_b200_slab_build_device   : resolves this rank's carries and runs the three passes on the local slab
  *   4. all-reduce(max) the two integers of sdf_b200_get_extrema_raw and convert with sdf_b200_extrema_from_raw.
- * slab_widths: host array, thickness (cells along z) of every rank's slab.  d_mask / d_sdf: local slab
- * (nx, ny, nz_local), z contiguous. */
+ * slab_widths: host array, thickness (cells along z) of every slab ("rank" = slab index; a process may own several
+ * slabs and build them one after the other -- keep_extrema != 0 then accumulates the per-polarity maxima onto those of
+ * the previous build on this context instead of restarting them).  d_mask / d_sdf: local slab (nx, ny, nz_local),
+ * z contiguous. */
 int sdf_b200_slab_summary_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
                                  uint32_t* d_summary);
 int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
                                double resolution, const uint32_t* d_all_summaries, const int32_t* slab_widths,
-                               int nranks, int rank, float* d_sdf);
+                               int nranks, int rank, int keep_extrema, float* d_sdf);
 /* Per-polarity maxima of the exact squared distance of the last build (0 = that polarity does not occur). */
 int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_t* out_max_filled_d2);
 /* (max, min) of sdf_generation.hpp:269 from (all-reduced) raw maxima. */

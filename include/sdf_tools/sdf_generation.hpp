@@ -15,6 +15,7 @@
 #pragma once
 #include <cstdint>
 #include <functional>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -24,6 +25,16 @@
 #include "sdf.hpp"
 
 namespace sdf_generation {
+
+// Per-voxel record of the reference's propagation (reference :19-27).  Only `distance_square` (and `location`) carry
+// meaning here: `closest_point` / `update_direction` are internals of the bucket-queue algorithm that is not run.
+struct bucket_cell {
+    double distance_square;
+    int32_t update_direction;
+    uint32_t location[3];
+    uint32_t closest_point[3];
+};
+typedef VoxelGrid::VoxelGrid<bucket_cell> DistanceField;
 
 namespace detail {
 // One context per host thread (the C ABI's contexts are not thread-safe; the reference is single-threaded).
@@ -58,6 +69,38 @@ BuildFromMask(const Eigen::Isometry3d& origin, double resolution, int64_t nx, in
     return std::make_pair(sdf, std::make_pair(mx, mn));
 }
 }  // namespace detail
+
+// Compatibility wrapper for the reference's public BuildDistanceField (:95-207): squared distance from every voxel to
+// the nearest of `points`, computed exactly on the GPU.  Throws std::runtime_error on an out-of-bounds seed (:133).
+inline DistanceField BuildDistanceField(const Eigen::Isometry3d& grid_origin_tranform, const double grid_resolution,
+                                        const int64_t grid_num_x_cells, const int64_t grid_num_y_cells,
+                                        const int64_t grid_num_z_cells, const std::vector<VoxelGrid::GRID_INDEX>& points) {
+    bucket_cell default_cell;
+    default_cell.distance_square = std::numeric_limits<double>::infinity();
+    default_cell.update_direction = -1;
+    for (int k = 0; k < 3; ++k) { default_cell.location[k] = 0; default_cell.closest_point[k] = 0; }
+    DistanceField field(grid_origin_tranform, grid_resolution, grid_num_x_cells, grid_num_y_cells, grid_num_z_cells, default_cell);
+    const int64_t nx = grid_num_x_cells, ny = grid_num_y_cells, nz = grid_num_z_cells;
+    std::vector<uint8_t> seeds((size_t)(nx * ny * nz), 0);
+    for (const VoxelGrid::GRID_INDEX& p : points) {
+        if (!field.IndexInBounds(p)) throw std::runtime_error("Point for BuildDistanceField out of bounds");
+        seeds[(size_t)((p.x * ny + p.y) * nz + p.z)] = 1;
+    }
+    std::vector<int32_t> s(seeds.size());
+    sdf_b200_ctx* ctx = detail::Context();
+    detail::Check(sdf_b200_signed_d2_from_mask(ctx, seeds.data(), nx, ny, nz, s.data()), ctx);
+    std::vector<bucket_cell>& cells = field.GetMutableRawData();
+    size_t i = 0;
+    for (int64_t x = 0; x < nx; ++x)
+        for (int64_t y = 0; y < ny; ++y)
+            for (int64_t z = 0; z < nz; ++z, ++i) {
+                bucket_cell& c = cells[i];
+                c.location[0] = (uint32_t)x; c.location[1] = (uint32_t)y; c.location[2] = (uint32_t)z;
+                const int32_t v = s[i];                       // > 0: free voxel, d2 to the nearest seed; < 0: a seed
+                c.distance_square = v < 0 ? 0.0 : (v >= SDF_B200_INF ? std::numeric_limits<double>::infinity() : (double)v);
+            }
+    return field;
+}
 
 // Dimensions + index predicate (reference :209-271).  T is unused, as in the reference.
 template <typename T>

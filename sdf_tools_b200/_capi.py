@@ -30,8 +30,9 @@ SYMBOLS = [
     ("sdf_b200_get_extrema", _int, [_vp, _pd, _pd]),
     ("sdf_b200_pack_cells_device", _int, [_vp, _vp, _i64, _int, _vp]),
     ("sdf_b200_signed_d2_device", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    ("sdf_b200_signed_d2_from_mask", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     ("sdf_b200_slab_summary_device", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
-    ("sdf_b200_slab_build_device", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _vp, C.POINTER(C.c_int32), _int, _int, _vp]),
+    ("sdf_b200_slab_build_device", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _vp, C.POINTER(C.c_int32), _int, _int, _int, _vp]),
     ("sdf_b200_get_extrema_raw", _int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("sdf_b200_extrema_from_raw", _int, [C.c_int32, C.c_int32, _dbl, _pd, _pd]),
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),

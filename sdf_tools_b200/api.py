@@ -111,11 +111,12 @@ class Context:
                                                            C.c_void_p(d_summary_ptr)))
 
     def slab_build_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, resolution: float,
-                          d_all_summaries_ptr: int, slab_widths, rank: int, d_sdf_ptr: int):
+                          d_all_summaries_ptr: int, slab_widths, rank: int, d_sdf_ptr: int, keep_extrema: bool = False):
         w = (C.c_int32 * len(slab_widths))(*[int(v) for v in slab_widths])
         self._check(self._lib.sdf_b200_slab_build_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz_local,
                                                          float(resolution), C.c_void_p(d_all_summaries_ptr), w,
-                                                         len(slab_widths), int(rank), C.c_void_p(d_sdf_ptr)))
+                                                         len(slab_widths), int(rank), int(bool(keep_extrema)),
+                                                         C.c_void_p(d_sdf_ptr)))
 
     def get_extrema_raw(self):
         a, b = C.c_int32(), C.c_int32()

@@ -159,12 +159,12 @@ int sdf_b200_host_free(void* p)
 
 // mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in place in d_field
 static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz, double res,
-                      int32_t* d_field, bool final_pass, const void* d_carries = nullptr)
+                      int32_t* d_field, bool final_pass, const void* d_carries = nullptr, bool keep_extrema = false)
 {
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
     ctx->timed = false;
-    CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
+    if (!keep_extrema) CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
     if (nx * ny * nz == 0) { ctx->built = true; ctx->res = res; return SDF_B200_OK; }
     constexpr int LUT_N = 1 << 20;                 // 4 MB: stays resident in the 126 MB L2
     if (final_pass && (ctx->d_lut == nullptr || ctx->lut_res != res)) {
@@ -231,7 +231,7 @@ int sdf_b200_slab_summary_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64
 
 int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
                                double resolution, const uint32_t* d_all_summaries, const int32_t* slab_widths,
-                               int nranks, int rank, float* d_sdf)
+                               int nranks, int rank, int keep_extrema, float* d_sdf)
 {
     if (!ctx) return SDF_B200_ERR_ARG;
     int rc = check_dims(ctx, nx, ny, nz_local);
@@ -251,9 +251,30 @@ int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t
            "launch slab_carry");
         carries = ctx->d_carries;
     }
-    rc = run_passes(ctx, d_mask, nx, ny, nz_local, resolution, reinterpret_cast<int32_t*>(d_sdf), true, carries);
+    rc = run_passes(ctx, d_mask, nx, ny, nz_local, resolution, reinterpret_cast<int32_t*>(d_sdf), true, carries,
+                    keep_extrema != 0);
     if (rc == SDF_B200_OK && carries) ctx->launches++;
     return rc;
+}
+
+int sdf_b200_signed_d2_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz, int32_t* out)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz);
+    if (rc) return rc;
+    const int64_t N = nx * ny * nz;
+    if (N == 0) return SDF_B200_OK;
+    if (!mask || !out) return fail(ctx, SDF_B200_ERR_ARG, "null host pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)N))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_mask, mask, (size_t)N, cudaMemcpyHostToDevice, st), "H2D mask");
+    rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, nx, ny, nz, 1.0, (int32_t*)ctx->d_out, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, st), "D2H d2");
+    CK(cudaStreamSynchronize(st), "sync");
+    return SDF_B200_OK;
 }
 
 int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_t* out_max_filled_d2)

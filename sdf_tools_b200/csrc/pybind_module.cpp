@@ -8,6 +8,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <array>
 #include <cstring>
 
 #include <sdf_tools/collision_map.hpp>
@@ -99,6 +100,19 @@ PYBIND11_MODULE(pysdf_tools, m) {
         .def("GetNumZCells", &CollisionMapGrid::GetNumZCells)
         .def("ExtractSignedDistanceField", &CollisionMapGrid::ExtractSignedDistanceField, py::arg("oob_value"),
              py::arg("unknown_is_filled"), py::arg("add_virtual_border"));
+
+    // sdf_generation::BuildDistanceField (compat wrapper): seeds as (x, y, z) triples -> flat distance_square array
+    m.def("BuildDistanceFieldD2", [](int64_t nx, int64_t ny, int64_t nz, const std::vector<std::array<int64_t, 3>>& seeds) {
+        std::vector<VoxelGrid::GRID_INDEX> pts;
+        pts.reserve(seeds.size());
+        for (const auto& s : seeds) pts.emplace_back(s[0], s[1], s[2]);
+        const sdf_generation::DistanceField f = sdf_generation::BuildDistanceField(Eigen::Isometry3d::Identity(), 1.0, nx, ny, nz, pts);
+        py::array_t<double> out({nx, ny, nz});
+        double* o = out.mutable_data();
+        const auto& d = f.GetImmutableRawData();
+        for (size_t i = 0; i < d.size(); ++i) o[i] = d[i].distance_square;
+        return out;
+    });
 
     py::class_<VoxelGridVecd>(m, "VoxelGrid")
         .def(py::init<>())

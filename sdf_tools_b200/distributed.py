@@ -114,47 +114,76 @@ def binary_z_np(mask_slab: np.ndarray, carry_lo=None, carry_hi=None) -> np.ndarr
 
 # ------------------------------------------------------------------------------------------------ device path
 class SlabBuilder:
-    """One rank of a slab-sharded build.  `group` is a torch.distributed process group (NCCL on GPUs)."""
+    """One rank of a slab-sharded build.  `group` is a torch.distributed process group (NCCL on GPUs).
 
-    def __init__(self, ctx, shape, rank: int, world: int, group=None):
+    The grid is cut into world * parts z slabs and dealt to the ranks cyclically (slab k belongs to rank k % world):
+    the envelope passes are data dependent, so one thick slab per rank leaves ranks with "busy" slabs behind; a few
+    thinner, interleaved slabs per rank even this out.  The exchange is unchanged -- per build one all-gather per
+    part index (the summaries of world consecutive slabs), and the carries are resolved over all world * parts slabs."""
+
+    def __init__(self, ctx, shape, rank: int, world: int, group=None, parts: int | None = None):
+        import os
         import torch
         self.torch = torch
         self.ctx = ctx
         self.nx, self.ny, self.nz = (int(v) for v in shape)
         self.rank, self.world, self.group = rank, world, group
-        self.ranges = slab_ranges(self.nz, world)
+        if parts is None:
+            parts = int(os.environ.get("SDF_B200_SLAB_PARTS", "2")) if world > 1 else 1
+        while parts > 1 and self.nz // (world * parts) < 32:
+            parts -= 1
+        self.parts = parts
+        self.nslabs = world * parts
+        self.ranges = slab_ranges(self.nz, self.nslabs)
         self.widths = [b - a for a, b in self.ranges]
-        self.z0, self.z1 = self.ranges[rank]
+        self.slab_ids = [p * world + rank for p in range(parts)]          # global slab index of each local part
+        self.local_ranges = [self.ranges[k] for k in self.slab_ids]
+        # single-part conveniences (the common N == 1 / parts == 1 case)
+        self.z0, self.z1 = self.local_ranges[0]
         self.nzl = self.z1 - self.z0
         dev = torch.device("cuda", ctx.device)
         nl = self.nx * self.ny
-        self.summary = torch.empty(nl, dtype=torch.int32, device=dev)
-        self.all_summaries = torch.empty(world * nl, dtype=torch.int32, device=dev)
-        self.raw = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.summary = torch.empty(parts * nl, dtype=torch.int32, device=dev)
+        self.all_summaries = torch.empty(self.nslabs * nl, dtype=torch.int32, device=dev)
 
-    def build(self, d_mask, resolution: float, d_sdf):
-        """d_mask: uint8 (nx, ny, nzl) device tensor of this rank's slab; d_sdf: float32 tensor of the same shape."""
+    def alloc_outputs(self):
+        torch = self.torch
+        dev = torch.device("cuda", self.ctx.device)
+        return [torch.empty((self.nx, self.ny, b - a), dtype=torch.float32, device=dev) for a, b in self.local_ranges]
+
+    def build(self, d_masks, resolution: float, d_sdfs):
+        """d_masks / d_sdfs: uint8 / float32 device tensors (nx, ny, width) of this rank's slabs, in self.slab_ids order
+        (a single tensor is accepted when the rank owns one slab)."""
         torch = self.torch
         import torch.distributed as dist
+        if not isinstance(d_masks, (list, tuple)):
+            d_masks, d_sdfs = [d_masks], [d_sdfs]
         ctx = self.ctx
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ctx.slab_summary_device(d_mask.data_ptr(), self.nx, self.ny, self.nzl, self.summary.data_ptr())
+        nl = self.nx * self.ny
+        for p, m in enumerate(d_masks):
+            w = self.widths[self.slab_ids[p]]
+            ctx.slab_summary_device(m.data_ptr(), self.nx, self.ny, w, self.summary[p * nl:].data_ptr())
         if self.world > 1:
-            dist.all_gather_into_tensor(self.all_summaries, self.summary, group=self.group)
+            for p in range(self.parts):     # slabs p*world .. p*world+world-1 are consecutive in the gathered buffer
+                dist.all_gather_into_tensor(self.all_summaries[p * self.world * nl:(p + 1) * self.world * nl],
+                                            self.summary[p * nl:(p + 1) * nl], group=self.group)
             src = self.all_summaries
         else:
             src = self.summary
-        ctx.slab_build_device(d_mask.data_ptr(), self.nx, self.ny, self.nzl, resolution, src.data_ptr(),
-                              self.widths, self.rank, d_sdf.data_ptr())
-        return d_sdf
+        for p, (m, o) in enumerate(zip(d_masks, d_sdfs)):
+            k = self.slab_ids[p]
+            ctx.slab_build_device(m.data_ptr(), self.nx, self.ny, self.widths[k], resolution, src.data_ptr(),
+                                  self.widths, k, o.data_ptr(), keep_extrema=(p > 0))
+        return d_sdfs
 
     def extrema(self, resolution: float):
         """Global (max, min): all-reduce(max) of the two raw integers, then the f64 conversion."""
         torch = self.torch
         import torch.distributed as dist
-        a, b = self.ctx.get_extrema_raw()
+        a, b = self.ctx.get_extrema_raw()              # maxima accumulated over this rank's slabs
         if self.world > 1:
-            t = torch.tensor([a, b], dtype=torch.int32, device=self.raw.device)
+            t = torch.tensor([a, b], dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             a, b = (int(v) for v in t.tolist())
         return self.ctx.extrema_from_raw(a, b, resolution)

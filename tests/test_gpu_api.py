@@ -114,3 +114,14 @@ def test_cpp_header_errors(P):
     grid = P.CollisionMapGrid(tf, "w", 0.5, 2049, 1, 1, P.COLLISION_CELL(0.0))
     with pytest.raises(RuntimeError):
         grid.ExtractSignedDistanceField(0.0, False, False)
+
+
+def test_build_distance_field_compat(P):
+    """sdf_generation::BuildDistanceField wrapper (reference sdf_generation.hpp:95-207): distance_square to the seeds."""
+    mask = synth.iid((20, 17, 13), 0.03, 8)
+    seeds = [tuple(int(v) for v in p) for p in np.argwhere(mask != 0)]
+    d2 = P.BuildDistanceFieldD2(20, 17, 13, seeds)
+    want = O.edt_d2(mask).astype(np.float64)
+    assert np.array_equal(d2, want)
+    with pytest.raises(RuntimeError):
+        P.BuildDistanceFieldD2(4, 4, 4, [(9, 0, 0)])          # out-of-bounds seed (:133)

@@ -151,12 +151,14 @@ def test_slab_builds_on_one_gpu(ctx):
         outs, raws = [], []
         for r, s in enumerate(slabs):
             o = torch.empty((nx, ny, widths[r]), dtype=torch.float32, device="cuda")
-            ctx.slab_build_device(s.data_ptr(), nx, ny, widths[r], 0.05, allsum.data_ptr(), widths, r, o.data_ptr())
+            ctx.slab_build_device(s.data_ptr(), nx, ny, widths[r], 0.05, allsum.data_ptr(), widths, r, o.data_ptr(),
+                                  keep_extrema=(r > 0))
             raws.append(ctx.get_extrema_raw())
             outs.append(o.cpu().numpy())
         got = np.concatenate(outs, axis=2)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"slab build differs ({mask.shape}, {nr} slabs)"
-        mx, mn = ctx.extrema_from_raw(max(a for a, _ in raws), max(b for _, b in raws), 0.05)
+        assert raws[-1] == (max(a for a, _ in raws), max(b for _, b in raws))      # accumulated across slabs
+        mx, mn = ctx.extrema_from_raw(*raws[-1], 0.05)
         assert (mx, mn) == (wmx, wmn)
 
 

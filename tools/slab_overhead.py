@@ -11,7 +11,7 @@ lr = int(os.environ.get("LOCAL_RANK", "0")); rank = int(os.environ["RANK"]); wor
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 cfg = synth.CONFIGS[wl]; nx, ny, nz = cfg["shape"]
-ctx = Context(lr); sb = SlabBuilder(ctx, (nx, ny, nz), rank, world)
+ctx = Context(lr); sb = SlabBuilder(ctx, (nx, ny, nz), rank, world, parts=1)
 mask = torch.from_numpy(synth.make_mask(wl, zrange=(sb.z0, sb.z1))).cuda()
 out = torch.empty((nx, ny, sb.nzl), dtype=torch.float32, device="cuda")
 ctx.set_stream(torch.cuda.current_stream().cuda_stream)
