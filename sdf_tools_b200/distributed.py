@@ -116,10 +116,11 @@ def binary_z_np(mask_slab: np.ndarray, carry_lo=None, carry_hi=None) -> np.ndarr
 class SlabBuilder:
     """One rank of a slab-sharded build.  `group` is a torch.distributed process group (NCCL on GPUs).
 
-    The grid is cut into world * parts z slabs and dealt to the ranks cyclically (slab k belongs to rank k % world):
-    the envelope passes are data dependent, so one thick slab per rank leaves ranks with "busy" slabs behind; a few
-    thinner, interleaved slabs per rank even this out.  The exchange is unchanged -- per build one all-gather per
-    part index (the summaries of world consecutive slabs), and the carries are resolved over all world * parts slabs."""
+    The grid is cut into world * parts z slabs and dealt to the ranks cyclically (slab k belongs to rank k % world).
+    parts > 1 (SDF_B200_SLAB_PARTS) interleaves several thinner slabs per rank to even out the data-dependent cost of
+    the envelope passes; measured on 8 B200 it did not pay (1024^3: 2.77 ms with 1 slab per rank vs 3.11 ms with 2;
+    2048x2048x1024: 16.8 vs 17.3 ms), so the default is one slab per rank.  The exchange is one all-gather per part
+    index (the summaries of world consecutive slabs); carries are resolved over all world * parts slabs."""
 
     def __init__(self, ctx, shape, rank: int, world: int, group=None, parts: int | None = None):
         import os
@@ -129,7 +130,7 @@ class SlabBuilder:
         self.nx, self.ny, self.nz = (int(v) for v in shape)
         self.rank, self.world, self.group = rank, world, group
         if parts is None:
-            parts = int(os.environ.get("SDF_B200_SLAB_PARTS", "2")) if world > 1 else 1
+            parts = int(os.environ.get("SDF_B200_SLAB_PARTS", "1")) if world > 1 else 1
         while parts > 1 and self.nz // (world * parts) < 32:
             parts -= 1
         self.parts = parts
