@@ -51,11 +51,12 @@ def load() -> C.CDLL:
     """Load libsdf_b200.so.  Fails loudly if it has not been built: there is no CPU or PyTorch fallback."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SDF_B200_LIB", LIB_PATH)      # override: A/B runs of kernel variants (tools/)
+        if not os.path.exists(path):
             raise LibraryMissing(
-                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  sdf_tools_b200 has no CPU fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, restype, argtypes in SYMBOLS:
             fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = restype

@@ -100,9 +100,12 @@ SDF_HD bool bh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t
 
 #if defined(BH_COUNT) && !defined(__CUDA_ARCH__)
 #define BH_TICK(x) (++bh_counters[x])
+#define BH_STEP() (++bh_serial)
 static long long bh_counters[8];
+static long long bh_serial;               // dependent shared-memory round trips (latency proxy)
 #else
 #define BH_TICK(x) ((void)0)
+#define BH_STEP() ((void)0)
 #endif
 constexpr int BH_BIG = 0x7fff;          // "no run boundary after": larger than any position
 
@@ -164,6 +167,7 @@ struct BandHull {
     // returns its slot (and the packed entry / the meta word of its band) or -1.
     static SDF_HD int first_from(const BandTile& T, int c, int b0, int ghi, uint32_t& e, uint32_t& m) {
         for (int b2 = b0; b2 < ghi; ++b2) {
+            BH_STEP();
             m = ldM(T, b2, c);
             if (m_hi(m) > m_lo(m)) {
                 const int u = (b2 << LOGB) + m_lo(m);
@@ -177,6 +181,7 @@ struct BandHull {
     // Last vertex of the run that leaves band b0 to the right (no polarity change after it), bands [glo, b0].
     static SDF_HD int last_upto(const BandTile& T, int c, int b0, int glo, uint32_t& e, uint32_t& m) {
         for (int b2 = b0; b2 >= glo; --b2) {
+            BH_STEP();
             m = ldM(T, b2, c);
             if (m_tail(m)) return -1;
             if (m_hi(m) > m_lo(m)) {
@@ -263,6 +268,7 @@ struct BandHull {
     // ------------------------------------------------------------------------------------------- phase merge
     // Round lv: (a) thread (c,b) with b = (2i+1)<<lv joins groups [b-2^lv, b) and [b, b+2^lv);
     //           (b) every thread advances the run-boundary doubling scans by distance 2^lv (buffers lv&1 -> (lv+1)&1).
+    static constexpr int JUMP_AFTER = 3;               // single steps before the tangent walk starts jumping
     static SDF_HD void merge(const BandTile& T, int c, int b, int nb, int lv) {
         // (b) scans: inclusive prefix-max of last run start, inclusive suffix-min of first run start
         {
@@ -322,28 +328,95 @@ struct BandHull {
         int Lp = u_pos(uL, eL), Rp = u_pos(uR, eR);
         int32_t LY = Lp * Lp + e_h(eL), RY = Rp * Rp + e_h(eR);
         bool dirtyL = false, dirtyR = false;
+        int nL = 0, nR = 0;                                // vertices dropped so far on each side
         for (;;) {
             bool changed = false;
             while (uL2 >= 0) {
                 const int L2p = u_pos(uL2, eL2);
                 const int32_t L2Y = L2p * L2p + e_h(eL2);
+                BH_STEP();
                 if (!bh_dominated(L2p, L2Y, Lp, LY, Rp, RY)) break;
-                BH_TICK(1 + (lv < 5 ? lv : 5));
-                if ((uL2 >> LOGB) != (uL >> LOGB))             // leaving a band: it is now empty
-                    stM(T, uL >> LOGB, c, (mLm & ~(127u << 8)) | ((uint32_t)m_lo(mLm) << 8));
-                uL = uL2; eL = eL2; mLm = mL2; Lp = L2p; LY = L2Y;
                 dirtyL = true; changed = true;
+                // L is dropped.  Dropped vertices form a SUFFIX of the left chain (the test is monotone along a convex
+                // chain), so jump instead of stepping when L's band holds a single run: first the whole band (its
+                // first vertex against its predecessor in an earlier band), else a binary search inside the band.
+                const int kL = uL & (B - 1), loL = m_lo(mLm), bL = uL >> LOGB;
+                if (++nL > JUMP_AFTER && !m_any(mLm) && kL - loL >= 2) {
+                    uint32_t eP = 0, mP = 0;
+                    const int uP = (bL > glo) ? last_upto(T, c, bL - 1, glo, eP, mP) : -1;
+                    const uint32_t eF = ldS(T, bL, loL, c);
+                    const int Fp = (bL << LOGB) + e_rel(eF);
+                    const int32_t FY = Fp * Fp + e_h(eF);
+                    bool whole = false;
+                    if (uP >= 0) {
+                        const int Pp = u_pos(uP, eP);
+                        whole = bh_dominated(Pp, Pp * Pp + e_h(eP), Fp, FY, Rp, RY);
+                    }
+                    if (whole) {
+                        BH_TICK(6);
+                        stM(T, bL, c, (mLm & ~(127u << 8)) | ((uint32_t)loL << 8));      // band now empty
+                        uL = uP; eL = eP; mLm = mP;
+                    } else {
+                        BH_TICK(7);
+                        int a = loL, z = kL;                   // v_a survives, v_z is dropped
+                        while (z - a > 1) {
+                            const int mid = (a + z) >> 1; BH_STEP();
+                            const uint32_t e0 = ldS(T, bL, mid - 1, c), e1 = ldS(T, bL, mid, c);
+                            const int p0 = (bL << LOGB) + e_rel(e0), p1 = (bL << LOGB) + e_rel(e1);
+                            if (bh_dominated(p0, p0 * p0 + e_h(e0), p1, p1 * p1 + e_h(e1), Rp, RY)) z = mid; else a = mid;
+                        }
+                        uL = (bL << LOGB) + a; eL = ldS(T, bL, a, c);
+                    }
+                    Lp = u_pos(uL, eL); LY = Lp * Lp + e_h(eL);
+                } else {
+                    BH_TICK(1 + (lv < 5 ? lv : 5));
+                    if ((uL2 >> LOGB) != bL)                       // leaving a band: it is now empty
+                        stM(T, bL, c, (mLm & ~(127u << 8)) | ((uint32_t)loL << 8));
+                    uL = uL2; eL = eL2; mLm = mL2; Lp = L2p; LY = L2Y;
+                }
                 uL2 = prev_of(T, c, glo, uL, eL, mLm, eL2, mL2);
             }
             while (uR2 >= 0) {
                 const int R2p = u_pos(uR2, eR2);
                 const int32_t R2Y = R2p * R2p + e_h(eR2);
+                BH_STEP();
                 if (!bh_dominated(Lp, LY, Rp, RY, R2p, R2Y)) break;
-                BH_TICK(1 + (lv < 5 ? lv : 5));
-                if ((uR2 >> LOGB) != (uR >> LOGB))
-                    stM(T, uR >> LOGB, c, (mRm & ~127u) | (uint32_t)m_hi(mRm));
-                uR = uR2; eR = eR2; mRm = mR2; Rp = R2p; RY = R2Y;
                 dirtyR = true; changed = true;
+                // R is dropped; dropped vertices form a PREFIX of the right chain: same jumps, mirrored.
+                const int kR = uR & (B - 1), hiR = m_hi(mRm), bR = uR >> LOGB;
+                if (++nR > JUMP_AFTER && !m_any(mRm) && hiR - 1 - kR >= 2) {
+                    uint32_t eN = 0, mN = 0;
+                    const int uN = (bR + 1 < ghi) ? first_from(T, c, bR + 1, ghi, eN, mN) : -1;
+                    const uint32_t eE = ldS(T, bR, hiR - 1, c);
+                    const int Ep = (bR << LOGB) + e_rel(eE);
+                    const int32_t EY = Ep * Ep + e_h(eE);
+                    bool whole = false;
+                    if (uN >= 0) {
+                        const int Np = u_pos(uN, eN);
+                        whole = bh_dominated(Lp, LY, Ep, EY, Np, Np * Np + e_h(eN));
+                    }
+                    if (whole) {
+                        BH_TICK(6);
+                        stM(T, bR, c, (mRm & ~127u) | (uint32_t)hiR);                      // band now empty
+                        uR = uN; eR = eN; mRm = mN;
+                    } else {
+                        BH_TICK(7);
+                        int a = kR, z = hiR - 1;               // v_a is dropped, v_z survives
+                        while (z - a > 1) {
+                            const int mid = (a + z) >> 1; BH_STEP();
+                            const uint32_t e0 = ldS(T, bR, mid, c), e1 = ldS(T, bR, mid + 1, c);
+                            const int p0 = (bR << LOGB) + e_rel(e0), p1 = (bR << LOGB) + e_rel(e1);
+                            if (bh_dominated(Lp, LY, p0, p0 * p0 + e_h(e0), p1, p1 * p1 + e_h(e1))) a = mid; else z = mid;
+                        }
+                        uR = (bR << LOGB) + z; eR = ldS(T, bR, z, c);
+                    }
+                    Rp = u_pos(uR, eR); RY = Rp * Rp + e_h(eR);
+                } else {
+                    BH_TICK(1 + (lv < 5 ? lv : 5));
+                    if ((uR2 >> LOGB) != bR)
+                        stM(T, bR, c, (mRm & ~127u) | (uint32_t)hiR);
+                    uR = uR2; eR = eR2; mRm = mR2; Rp = R2p; RY = R2Y;
+                }
                 uR2 = next_of(T, c, ghi, uR, mRm, eR2, mR2);
             }
             if (!changed) break;

@@ -10,6 +10,7 @@
 using namespace sdfb200;
 
 static uint64_t rng_state = 1;
+static long long merge_critical_path = 0;   // sum over tiles and rounds of the longest per-thread dependent chain
 static uint32_t rnd() { rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL; return (uint32_t)(rng_state >> 33); }
 
 // one strided pass in place: g[r*line_stride + c], r < n, c < ncols
@@ -43,7 +44,16 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
             }
             BH::build(T, c, b, (c0 + c < ncols) ? n : 0, prevpol, Pw[t], PCw[t]);
         }
-        for (int lv = 0; lv < nlevels; lv++) { shuf(); for (int t : order) BH::merge(T, t % LPC, t / LPC, nb, lv); }
+        for (int lv = 0; lv < nlevels; lv++) {
+            shuf();
+            long long worst = 0;
+            for (int t : order) {
+                const long long s0 = bh_serial;
+                BH::merge(T, t % LPC, t / LPC, nb, lv);
+                worst = std::max(worst, bh_serial - s0);
+            }
+            merge_critical_path += worst;              // the round ends when its slowest thread does
+        }
         shuf();
         for (int t : order) {
             const int b = t / LPC, c = t % LPC;
@@ -64,6 +74,8 @@ static int dispatch(int32_t* g, int n, int64_t ls, int64_t ncols, int shuffle, i
 }
 
 extern "C" {
+
+long long emul_band_merge_critical_path(int reset) { const long long v = merge_critical_path; if (reset) merge_critical_path = 0; return v; }
 
 void emul_band_counters(long long* out, int reset) { for (int i = 0; i < 8; i++) { out[i] = bh_counters[i]; if (reset) bh_counters[i] = 0; } }
 

@@ -99,3 +99,36 @@ def test_structured_configs(lib, name, shape):
     got = np.empty(shape, np.int32)
     assert lib.emul_band_signed_d2(m, *shape, got, 5, 16, 1, 3) == 0
     assert np.array_equal(got, O.signed_d2(m))
+
+
+def test_merge_jumps_on_plateaus(lib):
+    """Step / plateau height profiles (a box above a ground plane seen along y) make the seam merges drop hundreds of
+    consecutive vertices: the whole-band and in-band jumps of the tangent walk must be taken, and stay exact."""
+    rng = np.random.default_rng(11)
+    ctr = (C.c_longlong * 8)()
+    lib.emul_band_counters(ctr, 1)
+    for trial in range(30):
+        n = int(rng.choice([256, 500, 1024, 1500, 2048]))
+        lines = []
+        for _ in range(4):
+            h = np.full(n, int(rng.integers(100, 900)) ** 2, np.int64)
+            for _k in range(int(rng.integers(1, 4))):                   # low plateaus, pits and ramps
+                a = int(rng.integers(0, n)); w = int(rng.integers(1, max(2, n // 3)))
+                kind = rng.integers(0, 3)
+                if kind == 0: h[a:a + w] = int(rng.integers(1, 90)) ** 2
+                elif kind == 1: h[a:a + 1] = 1
+                else: h[a:a + w] = (np.arange(len(h[a:a + w])) + int(rng.integers(1, 50))) ** 2
+            pol = np.zeros(n, bool)
+            if rng.random() < 0.3:
+                a = int(rng.integers(0, n)); pol[a:a + int(rng.integers(1, 40))] = True
+            lines.append(np.where(pol, -h, h).astype(np.int32))
+        g = np.ascontiguousarray(np.stack(lines, axis=1))
+        want = np.stack([line_oracle(l) for l in lines], axis=1)
+        for logb, lpc in [(5, 16), (5, 8), (4, 4), (6, 8)]:
+            if n > (64 << logb):
+                continue
+            got = g.copy()
+            assert lib.emul_band_pass(got, n, 4, 4, logb, lpc, trial % 2, trial) == 0
+            assert np.array_equal(got, want), (n, logb, lpc)
+    lib.emul_band_counters(ctr, 0)
+    assert ctr[6] > 100 and ctr[7] > 100, list(ctr)        # whole-band jumps and in-band binary searches both ran
