@@ -140,10 +140,13 @@ struct BandHull {
     using pcw_t = typename std::conditional<(LOGB > 5), uint64_t, uint32_t>::type;
 
     // ---- packed hull entry ------------------------------------------------------------------------------
-    static SDF_HD uint32_t pack(int rel, int32_t h, bool rs) { return (uint32_t)h | ((uint32_t)rel << 24) | ((uint32_t)rs << 30); }
+    // {position in band : 6 (bits 26..31), first vertex of its run : 1 (bit 25), |s| : 24 (bits 0..23)}
+    static constexpr int REL_SHIFT = 26;
+    static constexpr uint32_t RS_BIT = 1u << 25;
+    static SDF_HD uint32_t pack(int rel, int32_t h, bool rs) { return (uint32_t)h | ((uint32_t)rel << REL_SHIFT) | (rs ? RS_BIT : 0u); }
     static SDF_HD int32_t e_h(uint32_t e) { return (int32_t)(e & 0xFFFFFFu); }
-    static SDF_HD int e_rel(uint32_t e) { return (int)((e >> 24) & 63u); }
-    static SDF_HD bool e_rs(uint32_t e) { return (e >> 30) & 1u; }
+    static SDF_HD int e_rel(uint32_t e) { return (int)(e >> REL_SHIFT); }
+    static SDF_HD bool e_rs(uint32_t e) { return (e & RS_BIT) != 0; }
     // ---- band meta ---------------------------------------------------------------------------------------
     static SDF_HD uint32_t mk_meta(int lo, int hi, bool tailpc, bool anypc, bool headpc) {
         return (uint32_t)lo | ((uint32_t)hi << 8) | ((uint32_t)tailpc << 16) | ((uint32_t)anypc << 17) | ((uint32_t)headpc << 18);
@@ -218,48 +221,69 @@ struct BandHull {
     // positions >= n): the hull is built IN PLACE -- vertex k <= i overwrites slot k after slot i has been read.
     // prevpol = polarity of position b*B - 1 (for b == 0: polarity of position 0).
     static SDF_HD void build(const BandTile& T, int c, int b, int n, bool prevpol, pcw_t& Pw, pcw_t& PCw) {
+        static_assert(LOGB <= 6, "32-bit hull tests inside a band need |dY| * |dq| < 2^31: dY < 2^25, dq < 2^LOGB");
         const int base = b << LOGB;
         int nvalid = n - base;
         nvalid = nvalid < 0 ? 0 : (nvalid > B ? B : nvalid);
-        const bh_addr_t st = T.S + 4u * (uint32_t)sidx(b, 0, c);   // this thread's slots: slot k at st + k*LPC*4
-        pcw_t pw = 0, pcw = 0;
-        int k = 0, cnt = 0;                           // vertices in the band / in the current run
-        int tp = 0, sp = 0, dPts = 1;
-        int32_t tY = 0, sY = 0, dYts = 0;
-        bool pcflag = false;                          // a run boundary since the previous vertex of this band
+        constexpr uint32_t STEP = LPC * 4;            // bytes between consecutive slots of this thread
+        const bh_addr_t st = T.S + 4u * (uint32_t)sidx(b, 0, c);
+        bh_addr_t rd = st;                            // slot of the position being read
+        bh_addr_t top = st;                           // slot the next vertex goes to
+        bh_addr_t bot = st;                           // slot of the first vertex of the current run
+        pcw_t pwr = 0;                                // polarity bits, shifted in from the right (bit-reversed)
+        int32_t vprev = prevpol ? -1 : 0;             // only its sign is used
+        int32_t pcacc = 0;                            // sign set <=> a run boundary since the previous vertex
+        // Hull in band-relative lifted coordinates (i, i^2 + h): differs from (q, q^2 + h) by an affine map, which
+        // leaves every hull test unchanged.  State: top vertex t = (tp, tY) and d = t - s to the vertex below it, or the
+        // sentinel d = (0, -1) that makes the test false while the run has fewer than two vertices (needs i > tp).
+        int tp = -1, dP = 0;
+        int32_t tY = 0, dY = -1;
 #pragma unroll 2
         for (int i = 0; i < nvalid; ++i) {
-            const int32_t v = (int32_t)bh_ld32(st + (uint32_t)(i * (LPC * 4)));
-            const bool pol = v < 0;
-            const int32_t h = pol ? -v : v;
-            if (pol != prevpol) { pcw |= (pcw_t)1 << i; pcflag = true; prevpol = pol; }
-            if (pol) pw |= (pcw_t)1 << i;
+            const int32_t v = (int32_t)bh_ld32(rd);
+            rd += STEP;
+            if (LOGB > 5) pwr = (pwr << 1) | (pcw_t)((uint32_t)v >> 31); else pwr = (pcw_t)bh_shift_in_sign((uint32_t)pwr, v);
+            pcacc |= v ^ vprev;
+            vprev = v;
+            const int32_t h = v < 0 ? -v : v;
             if (h < SDF_INF) {
-                if (pcflag) cnt = 0;
-                const int q = base + i;
-                const int32_t Y = q * q + h;
+                if (pcacc < 0) { bot = top; dY = -1; dP = 0; }
+                const int32_t Y = i * i + h;
                 int32_t A = Y - tY;
-                int Bq = q - tp;
-                while (cnt >= 2 && (long long)dYts * (long long)Bq >= (long long)A * (long long)dPts) {
-                    --k; --cnt; BH_TICK(0);
-                    tp = sp; tY = sY;
-                    if (cnt >= 2) {
-                        const uint32_t e = bh_ld32(st + (uint32_t)((k - 2) * (LPC * 4)));
-                        sp = base + e_rel(e);
-                        sY = sp * sp + e_h(e);
-                    }
-                    dYts = tY - sY; dPts = tp - sp;
-                    A = Y - tY; Bq = q - tp;
+                int Bq = i - tp;
+                while (dY * Bq >= A * dP) {           // t on or above the chord s -> new point: pop it
+                    BH_TICK(0);
+                    top -= STEP;
+                    tp -= dP; tY -= dY;               // t <- s
+                    if (top - bot >= 2 * STEP) {
+                        const uint32_t e = bh_ld32(top - 2 * STEP);
+                        const int sp = e_rel(e);
+                        dP = tp - sp; dY = tY - (sp * sp + e_h(e));
+                    } else { dY = -1; dP = 0; }
+                    A = Y - tY; Bq = i - tp;
                 }
-                bh_st32(st + (uint32_t)(k * (LPC * 4)), (uint32_t)h | ((uint32_t)i << 24) | ((uint32_t)pcflag << 30));
-                ++k; ++cnt;
-                sp = tp; sY = tY; tp = q; tY = Y;
-                dYts = A; dPts = Bq;
-                pcflag = false;
+                bh_st32(top, (uint32_t)h | ((uint32_t)i << REL_SHIFT) | (((uint32_t)pcacc >> 6) & RS_BIT));
+                if (top == bot) { dY = -1; dP = 0; } else { dY = A; dP = Bq; }   // first vertex of its run
+                top += STEP;
+                tp = i; tY = Y;
+                pcacc = 0;
             }
         }
+        // polarity / run-start words from the shifted-in signs: bit i of pw = polarity of position i
+        pcw_t pw;
+        if (LOGB > 5) {
+            const uint64_t r = (uint64_t)pwr;
+            pw = (pcw_t)(((uint64_t)bh_brev((uint32_t)r) << 32) | (uint64_t)bh_brev((uint32_t)(r >> 32)));
+        } else {
+            pw = (pcw_t)bh_brev((uint32_t)pwr);
+        }
+        pw = nvalid ? (pcw_t)(pw >> ((LOGB > 5 ? 64 : 32) - nvalid)) : (pcw_t)0;
+        const pcw_t valid = nvalid ? low_incl(nvalid - 1) : (pcw_t)0;
+        const pcw_t pcw = (pw ^ ((pcw_t)(pw << 1) | (pcw_t)(prevpol ? 1 : 0))) & valid;
+        const int k = (int)((top - st) / STEP);
         const bool anypc = pcw != 0;
-        stM(T, b, c, mk_meta(0, k, pcflag, anypc, (pcw & 1) != 0));
+        const bool tailpc = pcacc < 0;               // a run boundary after the band's last vertex
+        stM(T, b, c, mk_meta(0, k, tailpc, anypc, (pcw & 1) != 0));
         bh_st16(T.pcA + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_hi(pcw) : -1);
         bh_st16(T.pcE + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_lo(pcw) : BH_BIG);
         Pw = pw; PCw = pcw;
@@ -268,7 +292,7 @@ struct BandHull {
     // ------------------------------------------------------------------------------------------- phase merge
     // Round lv: (a) thread (c,b) with b = (2i+1)<<lv joins groups [b-2^lv, b) and [b, b+2^lv);
     //           (b) every thread advances the run-boundary doubling scans by distance 2^lv (buffers lv&1 -> (lv+1)&1).
-    static constexpr int JUMP_AFTER = 3;               // single steps before the tangent walk starts jumping
+    static constexpr int JUMP_AFTER = 2;               // single steps before the tangent walk starts jumping
     static SDF_HD void merge(const BandTile& T, int c, int b, int nb, int lv) {
         // (b) scans: inclusive prefix-max of last run start, inclusive suffix-min of first run start
         {
