@@ -118,20 +118,22 @@ SDF_HD uint32_t bh_ld32(bh_addr_t a) { uint32_t v; asm volatile("ld.shared.u32 %
 SDF_HD void bh_st32(bh_addr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 SDF_HD int bh_ld16(bh_addr_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 SDF_HD void bh_st16(bh_addr_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((short)v) : "memory"); }
+SDF_HD void bh_or32(bh_addr_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 #else
 typedef uintptr_t bh_addr_t;
 SDF_HD uint32_t bh_ld32(bh_addr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
 SDF_HD void bh_st32(bh_addr_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
 SDF_HD int bh_ld16(bh_addr_t a) { return *reinterpret_cast<const int16_t*>(a); }
 SDF_HD void bh_st16(bh_addr_t a, int v) { *reinterpret_cast<int16_t*>(a) = (int16_t)v; }
+SDF_HD void bh_or32(bh_addr_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) |= v; }     // emulation is sequential
 #endif
 
 struct BandTile {
     bh_addr_t S;      // uint32 [NB*B][LPC]  packed hull entries
     bh_addr_t meta;   // uint32 [NB][LPC]    lo:7 | hi:7 <<8 | tailPC <<16 | anyPC <<17 | headPC <<18
-    bh_addr_t pcA;    // int16  [2][NB][LPC] last run start inside bands <= b (double-buffered doubling scan)
-    bh_addr_t pcE;    // int16  [2][NB][LPC] first run start inside bands >= b
-    int pcstride;     // NB*LPC: elements between the two scan buffers
+    bh_addr_t pcA;    // int16  [NB][LPC]    last run start inside band b   (-1 if none)
+    bh_addr_t pcE;    // int16  [NB][LPC]    first run start inside band b  (BH_BIG if none)
+    bh_addr_t anyw;   // uint32 [NW][LPC]    bit (b & 31) of word (b >> 5): band b holds a run start; zeroed before build
 };
 
 template <int LOGB, int LPC>
@@ -284,71 +286,56 @@ struct BandHull {
         const bool anypc = pcw != 0;
         const bool tailpc = pcacc < 0;               // a run boundary after the band's last vertex
         stM(T, b, c, mk_meta(0, k, tailpc, anypc, (pcw & 1) != 0));
-        bh_st16(T.pcA + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_hi(pcw) : -1);
-        bh_st16(T.pcE + 2u * (uint32_t)midx(b, c), anypc ? base + pcw_lo(pcw) : BH_BIG);
+        if (anypc) {
+            bh_st16(T.pcA + 2u * (uint32_t)midx(b, c), base + pcw_hi(pcw));
+            bh_st16(T.pcE + 2u * (uint32_t)midx(b, c), base + pcw_lo(pcw));
+            bh_or32(T.anyw + 4u * (uint32_t)((b >> 5) * LPC + c), 1u << (b & 31));
+        }
         Pw = pw; PCw = pcw;
     }
 
     // ------------------------------------------------------------------------------------------- phase merge
-    // Round lv: (a) thread (c,b) with b = (2i+1)<<lv joins groups [b-2^lv, b) and [b, b+2^lv);
-    //           (b) every thread advances the run-boundary doubling scans by distance 2^lv (buffers lv&1 -> (lv+1)&1).
+    // Round lv: thread (c,b) with b = (2i+1)<<lv joins groups [b-2^lv, b) and [b, b+2^lv).  Round 0 only touches bands
+    // 2i and 2i+1, which the same warp built when 2*LPC <= 32: it then needs no CTA-wide barrier before it.
     static constexpr int JUMP_AFTER = 2;               // single steps before the tangent walk starts jumping
     static SDF_HD void merge(const BandTile& T, int c, int b, int nb, int lv) {
-        // (b) scans: inclusive prefix-max of last run start, inclusive suffix-min of first run start
-        {
-            const int d = 1 << lv, src = lv & 1, dst = src ^ 1;
-            const bh_addr_t As = T.pcA + 2u * (uint32_t)(src * T.pcstride), Ad = T.pcA + 2u * (uint32_t)(dst * T.pcstride);
-            const bh_addr_t Es = T.pcE + 2u * (uint32_t)(src * T.pcstride), Ed = T.pcE + 2u * (uint32_t)(dst * T.pcstride);
-            int a = bh_ld16(As + 2u * (uint32_t)midx(b, c));
-            if (b - d >= 0) { const int o = bh_ld16(As + 2u * (uint32_t)midx(b - d, c)); a = o > a ? o : a; }
-            bh_st16(Ad + 2u * (uint32_t)midx(b, c), a);
-            int e = bh_ld16(Es + 2u * (uint32_t)midx(b, c));
-            if (b + d < nb) { const int o = bh_ld16(Es + 2u * (uint32_t)midx(b + d, c)); e = o < e ? o : e; }
-            bh_st16(Ed + 2u * (uint32_t)midx(b, c), e);
-        }
-        // (a) seam
         const int g = 1 << lv;
         if ((b & (2 * g - 1)) != g) return;
         const uint32_t mR = ldM(T, b, c);
         if (m_head(mR)) return;                        // a run starts exactly at the seam
-        {   // fast path: the two bands next to the seam hold the bridge end points and nothing has to be dropped
+        const int glo = b - g;
+        int ghi = b + g; if (ghi > nb) ghi = nb;
+        // Two cursors walk the common tangent.  L / R = current bridge ends (slot, entry, band meta), L2 / R2 = their
+        // neighbours further inside (-1: none in the same run).  Bands are trimmed in registers and written back when left.
+        uint32_t eL = 0, mLm = 0, eR = 0, mRm = 0, eL2 = 0, mL2 = 0, eR2 = 0, mR2 = 0;
+        int uL = -1, uR = -1, uL2 = -1, uR2 = -1;
+        bool have = false;
+        {   // common case: the two bands next to the seam hold the bridge end points and their inner neighbours
             const uint32_t mL = ldM(T, b - 1, c);
             const int loR = m_lo(mR), hiR = m_hi(mR), loL = m_lo(mL), hiL = m_hi(mL);
             if (hiL > loL && !m_tail(mL) && hiR > loR) {
-                const uint32_t eL = ldS(T, b - 1, hiL - 1, c), eR = ldS(T, b, loR, c);
-                const uint32_t eL2 = ldS(T, b - 1, hiL >= 2 ? hiL - 2 : 0, c);
-                const uint32_t eR2 = ldS(T, b, loR + 1 < B ? loR + 1 : loR, c);
+                eL = ldS(T, b - 1, hiL - 1, c); eR = ldS(T, b, loR, c);
+                eL2 = ldS(T, b - 1, hiL >= 2 ? hiL - 2 : 0, c);
+                eR2 = ldS(T, b, loR + 1 < B ? loR + 1 : loR, c);
                 if (e_rs(eR)) return;                  // the run ends before the first vertex right of the seam
                 const bool simpleL2 = (hiL - 2 >= loL) && !e_rs(eL);
                 const bool noL2 = e_rs(eL);
                 const bool simpleR2 = loR + 1 < hiR;
                 if ((simpleL2 || noL2) && (simpleR2 || m_tail(mR))) {
-                    const int Lp = ((b - 1) << LOGB) + e_rel(eL), Rp = (b << LOGB) + e_rel(eR);
-                    const int32_t LYf = Lp * Lp + e_h(eL), RYf = Rp * Rp + e_h(eR);
-                    bool dom = false;
-                    if (simpleL2) {
-                        const int L2p = ((b - 1) << LOGB) + e_rel(eL2);
-                        dom = bh_dominated(L2p, L2p * L2p + e_h(eL2), Lp, LYf, Rp, RYf);
-                    }
-                    if (simpleR2 && !e_rs(eR2)) {
-                        const int R2p = (b << LOGB) + e_rel(eR2);
-                        dom = dom || bh_dominated(Lp, LYf, Rp, RYf, R2p, R2p * R2p + e_h(eR2));
-                    }
-                    if (!dom) return;
+                    have = true;
+                    uL = ((b - 1) << LOGB) + hiL - 1; mLm = mL; uL2 = simpleL2 ? uL - 1 : -1; mL2 = mL;
+                    uR = (b << LOGB) + loR; mRm = mR; uR2 = (simpleR2 && !e_rs(eR2)) ? uR + 1 : -1; mR2 = mR;
                 }
             }
         }
-        const int glo = b - g;
-        int ghi = b + g; if (ghi > nb) ghi = nb;
-        // general path: two cursors walk the common tangent.  L / R = current bridge ends (slot, entry, band meta),
-        // L2 / R2 = their neighbours further inside.  Bands are trimmed in registers and written back when left.
-        uint32_t eL, mLm, eR, mRm, eL2 = 0, mL2 = 0, eR2 = 0, mR2 = 0;
-        int uL = last_upto(T, c, b - 1, glo, eL, mLm);
-        if (uL < 0) return;
-        int uR = first_from(T, c, b, ghi, eR, mRm);
-        if (uR < 0) return;
-        int uL2 = prev_of(T, c, glo, uL, eL, mLm, eL2, mL2);
-        int uR2 = next_of(T, c, ghi, uR, mRm, eR2, mR2);
+        if (!have) {
+            uL = last_upto(T, c, b - 1, glo, eL, mLm);
+            if (uL < 0) return;
+            uR = first_from(T, c, b, ghi, eR, mRm);
+            if (uR < 0) return;
+            uL2 = prev_of(T, c, glo, uL, eL, mLm, eL2, mL2);
+            uR2 = next_of(T, c, ghi, uR, mRm, eR2, mR2);
+        }
         int Lp = u_pos(uL, eL), Rp = u_pos(uR, eR);
         int32_t LY = Lp * Lp + e_h(eL), RY = Rp * Rp + e_h(eR);
         bool dirtyL = false, dirtyR = false;
@@ -460,9 +447,20 @@ struct BandHull {
         if (base >= n) return;
         int nvalid = n - base;
         nvalid = nvalid > B ? B : nvalid;
-        const int fin = nlevels & 1;                        // buffer holding the finished scans
-        const int a0 = (b > 0) ? bh_ld16(T.pcA + 2u * (uint32_t)(fin * T.pcstride + midx(b - 1, c))) : -1;         // last run start before the band
-        const int e_after = (b + 1 < nb) ? bh_ld16(T.pcE + 2u * (uint32_t)(fin * T.pcstride + midx(b + 1, c))) : BH_BIG;   // first run start after it
+        (void)nlevels;
+        // nearest run start before / after the band, through the line's mask of bands that hold one
+        int a0 = -1, e_after = BH_BIG;
+        {
+            int w = b >> 5;
+            uint32_t m = bh_ld32(T.anyw + 4u * (uint32_t)(w * LPC + c)) & ((1u << (b & 31)) - 1u);
+            while (!m && w > 0) { --w; m = bh_ld32(T.anyw + 4u * (uint32_t)(w * LPC + c)); }
+            if (m) a0 = bh_ld16(T.pcA + 2u * (uint32_t)midx((w << 5) + bh_hibit(m), c));
+            w = b >> 5;
+            m = bh_ld32(T.anyw + 4u * (uint32_t)(w * LPC + c)) & ~((2u << (b & 31)) - 1u);
+            const int nw = (nb + 31) >> 5;
+            while (!m && w + 1 < nw) { ++w; m = bh_ld32(T.anyw + 4u * (uint32_t)(w * LPC + c)); }
+            if (m) e_after = bh_ld16(T.pcE + 2u * (uint32_t)midx((w << 5) + bh_lobit(m), c));
+        }
         const uint32_t mym = ldM(T, b, c);
         const int myhi = base + m_hi(mym);
         int us = base + m_lo(mym);                          // scan slot over this band's own vertices

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
                                                                  const float* __restrict__ lut, int lut_n,
-                                                                 const __grid_constant__ CUtensorMap tmap, int use_tma)
+                                                                 const __grid_constant__ CUtensorMap tmap, int tma_rows)
 {
     using BH = BandHull<LOGB, LPC>;
     // optional phase clocks (diagnostics): thread 0 of the first 1024 CTAs stores clock64() at phase boundaries
@@ -275,11 +275,12 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
         uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw);
         T.S = p;      p += (uint32_t)nb * B * LPC * 4;
         T.meta = p;   p += (uint32_t)nb * LPC * 4;
-        T.pcA = p;    p += (uint32_t)nb * LPC * 4;
-        T.pcE = p;
-        T.pcstride = nb * LPC;
+        T.pcA = p;    p += (uint32_t)nb * LPC * 2;
+        T.pcE = p;    p += (uint32_t)nb * LPC * 2;
+        T.anyw = p;
     }
     const int c = threadIdx.x % LPC, b = threadIdx.x / LPC;
+    if (b < (nb + 31) / 32) bh_st32(T.anyw + 4u * (uint32_t)(b * LPC + c), 0u);   // ordered before build by the barrier below
     const int64_t col = (int64_t)blockIdx.x * LPC + c;
     const bool col_ok = col < ncols;
     int32_t* gc = g + (int64_t)blockIdx.y * outer_stride + col;
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
     while ((1 << nlevels) < nb) ++nlevels;
 
     typename BH::pcw_t Pw, PCw;
-    if (use_tma) {
-        // Tile staging by TMA: one 3-D tensor-map box (LPC columns x 32 rows x 1) per band lands directly in the band's
+    if (tma_rows) {
+        // Tile staging by TMA: 3-D tensor-map boxes (LPC columns x tma_rows rows x 1, whole bands) land directly in the bands'
         // stack slots (the slot layout [row][line] IS the dense box layout); rows / columns outside the grid arrive as
         // zeros and are never read.  One thread arms an mbarrier with the byte count and issues the copies; everybody
         // waits on the barrier's phase.
@@ -303,10 +304,10 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
             const uint32_t bytes = (uint32_t)nb * B * LPC * 4u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
             const int c0 = (int)(blockIdx.x * LPC), o = (int)blockIdx.y;
-            for (int bb = 0; bb < nb; ++bb) {
-                const uint32_t dstp = T.S + (uint32_t)bb * (B * LPC * 4u);
+            for (int r0 = 0; r0 < nb * B; r0 += tma_rows) {       // boxes of LPC columns x tma_rows rows (whole bands)
+                const uint32_t dstp = T.S + (uint32_t)r0 * (LPC * 4u);
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             :: "r"(dstp), "l"(&tmap), "r"(c0), "r"(bb * B), "r"(o), "r"(bar) : "memory");
+                             :: "r"(dstp), "l"(&tmap), "r"(c0), "r"(r0), "r"(o), "r"(bar) : "memory");
             }
         }
         uint32_t done = 0;
@@ -343,12 +344,20 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
             prevpol = gc[(int64_t)qp * line_stride] < 0;
         }
         if (dbg_on) dbg[dbg_cta * 8 + 1] = clock64();
+        __syncthreads();
         BH::build(T, c, b, col_ok ? n : 0, prevpol, Pw, PCw);
     }
     if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
+    // Seam round 0 joins bands 2i and 2i+1: with <= 16 lines per CTA both were built by the same warp, so a warp-level
+    // barrier orders it after the build and one CTA-wide barrier is saved.
+    constexpr bool ROUND0_IN_WARP = (2 * LPC <= 32);
+    if (ROUND0_IN_WARP && nlevels > 0) {
+        __syncwarp();
+        BH::merge(T, c, b, nb, 0);
+    }
     __syncthreads();
     if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
-    for (int lv = 0; lv < nlevels; ++lv) {
+    for (int lv = ROUND0_IN_WARP ? 1 : 0; lv < nlevels; ++lv) {
         BH::merge(T, c, b, nb, lv);
         __syncthreads();
     }
@@ -468,7 +477,7 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
     constexpr int B = 1 << LOGB;
     const int nb = (n + B - 1) / B;
     if (nb > NBMAX) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)nb * B * LPC * 4 + (size_t)nb * LPC * 4 + (size_t)nb * LPC * 8;
+    const size_t smem = (size_t)nb * B * LPC * 4 + (size_t)nb * LPC * 4 + (size_t)nb * LPC * 4 + (size_t)((nb + 31) / 32) * LPC * 4;
     auto kern = band_strided_kernel<LOGB, LPC, NBMAX, FINAL>;
     if (smem > 48 * 1024) {   // per-device attribute; cheap enough to set on every launch
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -478,7 +487,7 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
     // 3-D tensor map of the pass's view of the field: (columns, rows along the axis, outer blocks), box = LPC x B x 1.
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    int use_tma = 0;
+    int tma_rows = 0;                                 // rows per tensor-map box; 0 = LDG staging
     static int tma_knob = -1;                         // SDF_B200_TMA=0 forces the LDG staging path
     if (tma_knob < 0) { const char* e = getenv("SDF_B200_TMA"); tma_knob = (e && e[0] == '0') ? 0 : 1; }
     const int64_t ostride = nouter > 1 ? outer_stride : line_stride * (int64_t)n;
@@ -486,14 +495,17 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
         (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
         const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)n, (cuuint64_t)nouter};
         const cuuint64_t gstr[2] = {(cuuint64_t)line_stride * 4u, (cuuint64_t)ostride * 4u};
-        const cuuint32_t box[3] = {(cuuint32_t)LPC, (cuuint32_t)B, 1u};
+        int bpb = 1;                                  // bands per box: the largest divisor of nb with <= 256 rows
+        for (int d = 2; d * B <= 256; ++d) if (nb % d == 0) bpb = d;
+        tma_rows = bpb * B;
+        const cuuint32_t box[3] = {(cuuint32_t)LPC, (cuuint32_t)tma_rows, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, g, gdim, gstr, box, estr,
                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        use_tma = (r == CUDA_SUCCESS) ? 1 : 0;
+        if (r != CUDA_SUCCESS) tma_rows = 0;
     }
-    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, use_tma);
+    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, tma_rows);
     return cudaGetLastError();
 }
 

@@ -22,14 +22,16 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
     const int nb = (n + B - 1) / B;
     int nlevels = 0; while ((1 << nlevels) < nb) ++nlevels;
     std::vector<uint32_t> S((size_t)nb * B * LPC), meta((size_t)nb * LPC);
-    std::vector<int16_t> a01((size_t)2 * nb * LPC), e01((size_t)2 * nb * LPC);
-    BandTile T; T.S = (bh_addr_t)S.data(); T.meta = (bh_addr_t)meta.data(); T.pcA = (bh_addr_t)a01.data(); T.pcE = (bh_addr_t)e01.data(); T.pcstride = nb * LPC;
+    std::vector<int16_t> a01((size_t)nb * LPC), e01((size_t)nb * LPC);
+    std::vector<uint32_t> anyw((size_t)((nb + 31) / 32) * LPC);
+    BandTile T; T.S = (bh_addr_t)S.data(); T.meta = (bh_addr_t)meta.data(); T.pcA = (bh_addr_t)a01.data(); T.pcE = (bh_addr_t)e01.data(); T.anyw = (bh_addr_t)anyw.data();
     std::vector<typename BH::pcw_t> Pw((size_t)nb * LPC), PCw((size_t)nb * LPC);
     std::vector<int> order((size_t)nb * LPC);
     for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
     auto shuf = [&]() { if (shuffle) for (size_t i = order.size() - 1; i > 0; i--) std::swap(order[i], order[rnd() % (i + 1)]); };
     std::vector<int32_t> outbuf((size_t)n * LPC);
     for (int64_t c0 = 0; c0 < ncols; c0 += LPC) {
+        std::fill(anyw.begin(), anyw.end(), 0u);
         shuf();
         for (int t : order) {
             const int b = t / LPC, c = t % LPC;
