@@ -13,19 +13,23 @@
 // The last term is the lower envelope of parabolas == lower convex hull of the lifted points (q, q^2 + |s(q)|).
 //
 // Per tile = LPC adjacent lines x n positions, thread (line c, band b):
-//   phase build   sequential hull (Felzenszwalb stack) of the band's own positions; the stack lives in shared memory
-//                 at S[(b*B + k)*LPC + c] -- bank == line, so lanes never conflict whatever their stack depths --
-//                 as packed words {|s| : 24, position-in-band : 6, first-of-run flag : 1}.  Restarted at every
-//                 polarity change.
+//   phase build   sequential hull (Felzenszwalb stack) of the band's own positions, in band-relative lifted
+//                 coordinates (i, i^2 + |s|) so that every test is a pair of 32-bit multiplies; the stack lives in
+//                 shared memory at S[(b*B + k)*LPC + c], built IN PLACE over the band's staged values, as packed words
+//                 {position-in-band : 6, first-of-run flag : 1, |s| : 24}.  Restarted at every polarity change.  Bands
+//                 that hold a run start set their bit in the line's band mask (anyw).
 //   phase merge   log2(NB) rounds; round lv joins band groups of 2^lv pairwise by walking the common tangent
-//                 across the seam (only when a run continues across it); trims band stacks from their ends.
-//                 The same rounds run a doubling scan that gives every band the nearest run boundary before/after it.
+//                 across the seam (only when a run continues across it); trims band stacks from their ends.  A walk
+//                 that keeps dropping switches to jumps: whole bands, then a binary search inside the last band.
 //   phase query   each thread walks the finished hull for its own band's positions (monotone minimiser),
-//                 adds the two run-end terms and writes the result row (coalesced across lines).
+//                 adds the two run-end terms (nearest run starts through the band mask) and writes the result row
+//                 (coalesced across lines).
 // Phases only communicate through the shared arrays and are race-free inside a phase, so the same functions run on
-// the GPU (separated by __syncthreads) and, for tests without a GPU, on the CPU as plain loops over (c, b).
+// the GPU (separated by __syncthreads; seam round 0 by __syncwarp when a warp holds both bands) and, for tests without
+// a GPU, on the CPU as plain loops over (c, b).
 //
-// Exactness: all integer.  |s| <= 3*2048^2 < 2^24, lifted heights < 2^25, hull tests cross-multiplied in int64.
+// Exactness: all integer.  |s| <= 3*2048^2 < 2^24, lifted heights < 2^25; hull tests inside a band fit 32 bits
+// (|dY| < 2^25, |dq| < 2^LOGB <= 64), tests across bands are cross-multiplied in int64.
 #pragma once
 #include <stdint.h>
 #include <type_traits>

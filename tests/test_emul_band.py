@@ -132,3 +132,37 @@ def test_merge_jumps_on_plateaus(lib):
             assert np.array_equal(got, want), (n, logb, lpc)
     lib.emul_band_counters(ctr, 0)
     assert ctr[6] > 100 and ctr[7] > 100, list(ctr)        # whole-band jumps and in-band binary searches both ran
+
+
+def test_ties_and_collinear_profiles(lib):
+    """Heights from tiny alphabets and exact parabolas make many hull tests come out EQUAL (collinear lifted points,
+    equal candidates): the >= / <= conventions of build, seam walks (single steps, whole-band jumps, in-band binary
+    searches) and query must agree with the definition on every one of them."""
+    rng = np.random.default_rng(23)
+    INF = O.INF
+    for trial in range(120):
+        n = int(rng.choice([7, 32, 33, 64, 96, 128, 129, 200, 256, 400]))
+        kind = trial % 6
+        q = np.arange(n, dtype=np.int64)
+        if kind == 0:   h = rng.integers(1, 3, n)                                   # {1, 2}
+        elif kind == 1: h = np.full(n, int(rng.integers(1, 5000)))                   # flat: every site is a vertex
+        elif kind == 2: h = (q - int(rng.integers(-5, n + 5))) ** 2 + int(rng.integers(1, 4))      # one exact parabola: all collinear after lifting
+        elif kind == 3: h = np.minimum((q - int(rng.integers(0, n))) ** 2, (q - int(rng.integers(0, n))) ** 2) + 1   # two parabolas
+        elif kind == 4: h = np.where(rng.random(n) < 0.5, 1, (q % 7 + 1) ** 2)
+        else:           h = np.where(rng.random(n) < 0.2, INF, rng.integers(1, 4, n))
+        h = np.minimum(h, INF)
+        pol = np.zeros(n, bool)
+        if trial % 3 == 0:
+            x = 0
+            while x < n:
+                L = int(rng.integers(1, max(2, n // 3))); pol[x:x + L] = rng.random() < 0.4; x += L
+        s = np.where(pol, -h, h).astype(np.int32)
+        want = line_oracle(s)
+        g = np.ascontiguousarray(np.stack([s, s[::-1].copy()], axis=1))
+        want2 = np.stack([want, line_oracle(s[::-1].copy())], axis=1)
+        for logb, lpc in [(3, 4), (4, 4), (5, 16), (6, 8)]:
+            if n > (64 << logb):
+                continue
+            got = g.copy()
+            assert lib.emul_band_pass(got, n, 2, 2, logb, lpc, trial % 2, trial) == 0
+            assert np.array_equal(got, want2), (n, kind, logb, lpc)
