@@ -130,6 +130,12 @@ int sdf_b200_last_launches(const sdf_b200_ctx* ctx);
  * then pass 3) receives them.  enable = 0 frees the buffer.  Not for production use. */
 int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, int n);
 
+/* Diagnostics: the final pass's distance arithmetic alone.  out[i] = the f32 the build stores for a voxel whose signed
+ * squared distance is m0 + i (i < count; host buffer), i.e. (float)(sqrt((double)|m|) * resolution) with the sign of
+ * m (sdf_generation.hpp:254-265).  Lets tests compare the device's FP64 sequence with the host's IEEE sqrt over whole
+ * ranges of m. */
+int sdf_b200_debug_distance_values(sdf_b200_ctx* ctx, int32_t m0, int32_t count, double resolution, float* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,7 @@ SYMBOLS = [
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),
     ("sdf_b200_last_launches", _int, [_vp]),
     ("sdf_b200_debug_phase_clocks", _int, [_vp, _int, C.POINTER(C.c_longlong), _int]),
+    ("sdf_b200_debug_distance_values", _int, [_vp, C.c_int32, C.c_int32, _dbl, _vp]),
 ]
 
 _lib = None

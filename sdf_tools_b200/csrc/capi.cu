@@ -469,4 +469,17 @@ int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, i
     return SDF_B200_OK;
 }
 
+int sdf_b200_debug_distance_values(sdf_b200_ctx* ctx, int32_t m0, int32_t count, double resolution, float* out)
+{
+    if (!ctx || count < 0 || (count > 0 && !out)) return SDF_B200_ERR_ARG;
+    if (count == 0) return SDF_B200_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    int rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)count * 4);
+    if (rc) return rc;
+    CK(sdfb200::launch_sqrt_check(m0, count, resolution, (float*)ctx->d_out, ctx->stream), "launch sqrt_check");
+    CK(cudaMemcpyAsync(out, ctx->d_out, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H values");
+    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    return SDF_B200_OK;
+}
+
 }  // extern "C"

@@ -14,6 +14,7 @@
 // envelope passes then both run along strided axes, where 32 adjacent lines are 32 adjacent addresses.
 #include "edt_kernels.cuh"
 #include "band_hull.cuh"
+#include "run_hull.cuh"
 
 #include <cuda.h>            // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched at run time (no -lcuda)
 #include <cuda_runtime.h>
@@ -394,6 +395,177 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
     }
 }
 
+
+// ========================================================================================= K2/K3 run hull
+// Envelope pass along a strided axis with the alive-mask hulls of run_hull.cuh: tile = LPC adjacent columns x n rows,
+// staged once (TMA) and never rewritten; thread (c, b) builds and queries band b of column c, seam merges are packed
+// onto the first threads.  In place in global memory.  FINAL fuses the reference's combine loop
+// (sdf_generation.hpp:246-268): (float)(sqrt((double)d2) * res) with the polarity sign, plus the extrema of the
+// signed d2 for the (max, min) pair returned at :269.
+
+// (float)(sqrt((double)m) * res) for 1 <= m < 2^25, bit for bit: rsqrt seed (2^-22) -> one coupled Goldschmidt step in
+// FP64 (g ~ sqrt m, h ~ 1/(2 sqrt m) to ~2^-43) -> one Markstein correction g + (m - g*g)*h, which rounds correctly
+// (checked exhaustively for m < 2^25 with perturbed seeds in tests/test_sqrt_sequence.py and on the device in
+// tests/test_gpu_parity.py).  Ten FP64-pipe instructions instead of the ~40 of the IEEE sqrt.f64 sequence.
+__device__ __forceinline__ float sdf_dist_f32(int32_t m, double res)
+{
+    float rf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)m));
+    const double x = (double)m, r = (double)rf;
+    double gq = x * r, h = 0.5 * r;
+    const double e = fma(-gq, h, 0.5);
+    gq = fma(gq, e, gq);
+    h = fma(h, e, h);
+    const double d = fma(-gq, gq, x);
+    gq = fma(d, h, gq);
+    return (float)(gq * res);
+}
+
+__device__ __forceinline__ float sdf_from_signed_d2_fast(int32_t s, double res)
+{
+    const int32_t m = s < 0 ? -s : s;
+    float f;
+    if (m < (1 << 25)) f = sdf_dist_f32(m, res);
+    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+    return __int_as_float(__float_as_int(f) | (s & 0x80000000));
+}
+
+__global__ void __launch_bounds__(256) sqrt_check_kernel(int32_t m0, int32_t count, double res, float* __restrict__ out)
+{
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = sdf_from_signed_d2_fast(m0 + i, res);
+}
+
+template <int LPC, int NBMAX, int NW, bool FINAL, bool USE_LUT>
+__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : ((NBMAX * LPC == 256) ? 6 : ((NBMAX * LPC == 128) ? 8 : 1)))
+run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, int64_t ncols, int64_t outer_stride,
+                   double res, int* __restrict__ ext, long long* __restrict__ dbg, const float* __restrict__ lut, int lut_n,
+                   const __grid_constant__ CUtensorMap tmap, int tma_rows)
+{
+    using RH = RunHull<LPC, NW>;
+    constexpr int B = 32;
+    const unsigned dbg_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned dbg_stride = (gridDim.x * gridDim.y + 1023u) / 1024u;            // sample ~1024 CTAs evenly
+    const int dbg_cta = (int)(dbg_lin / dbg_stride);
+    const bool dbg_on = dbg != nullptr && threadIdx.x == 0 && (dbg_lin % dbg_stride) == 0 && dbg_cta < 1024;
+    if (dbg_on) dbg[dbg_cta * 8 + 0] = clock64();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long tma_bar;
+    RunTile T;
+    {
+        uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw);
+        T.S = p;    p += (uint32_t)nb * B * LPC * 4;
+        T.AW = p;   p += (uint32_t)nb * LPC * 4;
+        T.PC = p;   p += (uint32_t)nb * LPC * 4;
+        T.NE = p;   p += (uint32_t)NW * LPC * 4;
+        T.PCS = p;
+    }
+    const int c = threadIdx.x % LPC, b = threadIdx.x / LPC;
+    if (threadIdx.x < 2 * NW * LPC) rh_st32(T.NE + 4u * threadIdx.x, 0u);           // NE and PCS are adjacent
+    const int64_t col = (int64_t)blockIdx.x * LPC + c;
+    const bool col_ok = col < ncols;
+    int32_t* gc = g + (int64_t)blockIdx.y * outer_stride + col;
+    const int base = b << 5;
+    int nlevels = 0;
+    while ((1 << nlevels) < nb) ++nlevels;
+
+    if (tma_rows) {
+        // Tile staging by TMA: 3-D tensor-map boxes (LPC columns x tma_rows rows x 1) land in the tile's [row][line]
+        // layout; rows / columns outside the grid arrive as zeros and are never read.
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)nb * B * LPC * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            const int c0 = (int)(blockIdx.x * LPC), o = (int)blockIdx.y;
+            for (int r0 = 0; r0 < nb * B; r0 += tma_rows) {
+                const uint32_t dstp = T.S + (uint32_t)r0 * (LPC * 4u);
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             :: "r"(dstp), "l"(&tmap), "r"(c0), "r"(r0), "r"(o), "r"(bar) : "memory");
+            }
+        }
+        uint32_t done = 0;
+        int spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+            if (!done && ++spins > (1 << 22)) __trap();       // never hang the device on a mis-programmed copy
+        }
+    } else {
+        // unaligned views: stage the band's values with plain loads
+        const rh_addr_t slot0 = RH::s_addr(T, base, c);
+        constexpr int U = 8;
+#pragma unroll
+        for (int i0 = 0; i0 < B; i0 += U) {
+            int32_t tmp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + i0 + u;
+                tmp[u] = (col_ok && q < n) ? gc[(int64_t)q * line_stride] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rh_st32(slot0 + (uint32_t)((i0 + u) * (LPC * 4)), (uint32_t)tmp[u]);
+        }
+        __syncthreads();
+    }
+    asm volatile("" : "+r"(T.S) :: "memory");                 // tile reads below may not move above the wait
+    if (dbg_on) dbg[dbg_cta * 8 + 1] = clock64();
+    uint32_t Pw, PCw;
+    RH::build(T, c, b, col_ok ? n : 0, Pw, PCw);
+    if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
+    __syncthreads();
+    if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
+    for (int lv = 0; lv < nlevels; ++lv) {
+        // seam tasks of this round, packed onto the first threads: task = (line, seam)
+        const int seam = ((int)(threadIdx.x / LPC) * 2 + 1) << lv;
+        if (seam < nb) RH::merge(T, c, seam, nb, lv, col_ok ? n : 0);
+        __syncthreads();
+    }
+    if (dbg_on) dbg[dbg_cta * 8 + 4] = clock64();
+    int32_t smax = 0, smin = 0;
+    if (col_ok) {
+        int32_t* dst = gc + (int64_t)base * line_stride;
+        constexpr int U = 4;                                   // results leave in groups: independent sqrt chains, batched stores
+        RH::template query<U>(T, c, b, nb, n, Pw, PCw, [&](int i0, const int32_t (&v)[U], int cnt) {
+            (void)i0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (u < cnt) {
+                    if (FINAL) {
+                        smax = max(smax, v[u]); smin = min(smin, v[u]);
+                        float f;
+                        if (USE_LUT) {
+                            const int32_t m = v[u] < 0 ? -v[u] : v[u];
+                            if (m < lut_n) f = __ldg(lut + m);
+                            else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+                            f = __int_as_float(__float_as_int(f) | (v[u] & 0x80000000));
+                        } else f = sdf_from_signed_d2_fast(v[u], res);
+                        dst[(int64_t)u * line_stride] = __float_as_int(f);
+                    } else {
+                        dst[(int64_t)u * line_stride] = v[u];
+                    }
+                }
+            }
+            dst += (int64_t)U * line_stride;
+        });
+    }
+    if (dbg_on) dbg[dbg_cta * 8 + 5] = clock64();
+    if (FINAL) {
+        // extrema of the signed d2 over the threads of the warp that exist (blockDim need not be a multiple of 32)
+        const unsigned live = __activemask();
+        smax = __reduce_max_sync(live, smax);
+        smin = __reduce_min_sync(live, smin);
+        if ((int)(threadIdx.x & 31) == __ffs((int)live) - 1) {
+            if (smax > 0) atomicMax(ext + 0, smax);
+            if (smin < 0) atomicMax(ext + 1, -smin);
+        }
+    }
+}
+
 // ================================================================================================ launchers
 cudaError_t launch_pack_cells(const void* d_cells, int64_t n, int unknown_is_filled, uint8_t* d_mask, cudaStream_t st)
 {
@@ -509,8 +681,68 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
     return cudaGetLastError();
 }
 
-// Tile shapes: bands of 32 rows everywhere; lines per CTA chosen so a CTA has <= 512 threads and ~64 KB of stacks
-// (3 CTAs per SM): n <= 256 -> 32 lines x <= 8 bands, n <= 1024 -> 16 lines x <= 32 bands, n <= 2048 -> 8 lines x <= 64 bands.
+// Tensor map of one pass's view of the field: (columns, rows along the axis, outer blocks), box = LPC x rows x 1.
+// Returns the rows per box (0: the view is not TMA-addressable -> plain loads).
+static int make_tile_map(CUtensorMap* tmap, int32_t* g, int n, int nb, int lpc, int64_t line_stride, int64_t ncols,
+                         int64_t nouter, int64_t outer_stride)
+{
+    memset(tmap, 0, sizeof(*tmap));
+    static int tma_knob = -1;                         // SDF_B200_TMA=0 forces the LDG staging path
+    if (tma_knob < 0) { const char* e = getenv("SDF_B200_TMA"); tma_knob = (e && e[0] == '0') ? 0 : 1; }
+    const int64_t ostride = nouter > 1 ? outer_stride : line_stride * (int64_t)n;
+    if (!(tma_knob && tensor_map_encoder() && (line_stride % 4) == 0 && (ostride % 4) == 0 &&
+          (reinterpret_cast<uintptr_t>(g) & 15) == 0))
+        return 0;
+    const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)n, (cuuint64_t)nouter};
+    const cuuint64_t gstr[2] = {(cuuint64_t)line_stride * 4u, (cuuint64_t)ostride * 4u};
+    int bpb = 1;                                      // bands per box: the largest divisor of nb with <= 256 rows
+    for (int d = 2; d * 32 <= 256; ++d) if (nb % d == 0) bpb = d;
+    const int rows = bpb * 32;
+    const cuuint32_t box[3] = {(cuuint32_t)lpc, (cuuint32_t)rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = tensor_map_encoder()(tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, g, gdim, gstr, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? rows : 0;
+}
+
+template <int LPC, int NBMAX, int NW, bool FINAL, bool USE_LUT>
+static cudaError_t launch_run_cfg(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
+                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
+                                  cudaStream_t st)
+{
+    const int nb = (n + 31) / 32;
+    if (nb > NBMAX) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)nb * 32 * LPC * 4 + (size_t)nb * LPC * 8 + (size_t)NW * LPC * 8;
+    auto kern = run_strided_kernel<LPC, NBMAX, NW, FINAL, USE_LUT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((unsigned)((ncols + LPC - 1) / LPC), (unsigned)nouter);
+    CUtensorMap tmap;
+    const int tma_rows = make_tile_map(&tmap, g, n, nb, LPC, line_stride, ncols, nouter, outer_stride);
+    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, tma_rows);
+    return cudaGetLastError();
+}
+
+// Tile shapes: lines per CTA chosen so that a CTA has <= 512 threads and <= 64 KB of tile (3 CTAs per SM at the large sizes).
+template <bool FINAL, bool USE_LUT>
+static cudaError_t launch_run_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
+                                int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
+                                cudaStream_t st)
+{
+#define RUN_CFG(LPC, NBMAX, NW) return launch_run_cfg<LPC, NBMAX, NW, FINAL, USE_LUT>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st)
+    if (n <= 128) RUN_CFG(32, 4, 1);
+    if (n <= 256) RUN_CFG(32, 8, 1);
+    if (n <= 512) RUN_CFG(32, 16, 1);
+    if (n <= 1024) RUN_CFG(16, 32, 1);
+    if (n <= 2048) RUN_CFG(8, 64, 2);
+#undef RUN_CFG
+    return cudaErrorInvalidValue;
+}
+
+// Tile shapes (old band kernel): bands of 32 rows everywhere; lines per CTA chosen so a CTA has <= 512 threads and ~64 KB of stacks
 template <bool FINAL>
 static cudaError_t launch_band_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
@@ -526,8 +758,22 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
                                 int64_t outer_stride, bool final_pass, double res, int* d_ext, long long* d_dbg,
                                 const float* d_lut, int lut_n, cudaStream_t st)
 {
-    return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
-                      : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
+    static int hull = -1, sq = -1;                    // experiment knobs: SDF_B200_HULL=band|run, SDF_B200_SQRT=lut|fp64
+    if (hull < 0) { const char* e = getenv("SDF_B200_HULL"); hull = (e && e[0] == 'b') ? 0 : 1; }
+    if (sq < 0) { const char* e = getenv("SDF_B200_SQRT"); sq = (e && e[0] == 'l') ? 0 : 1; }
+    if (hull == 0)
+        return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
+                          : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
+    if (!final_pass) return launch_run_f<false, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
+    return sq ? launch_run_f<true, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
+              : launch_run_f<true, true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
+}
+
+cudaError_t launch_sqrt_check(int32_t m0, int32_t count, double res, float* d_out, cudaStream_t st)
+{
+    if (count <= 0) return cudaSuccess;
+    sqrt_check_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(m0, count, res, d_out);
+    return cudaGetLastError();
 }
 
 }  // namespace sdfb200

@@ -30,4 +30,7 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
 // d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution
 cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st);   // d_dbg: optional 2 x 1024 x 8 phase clocks (diagnostics), or NULL
 
+// out[i] = the final pass's distance value for signed d2 = m0 + i (diagnostics / tests)
+cudaError_t launch_sqrt_check(int32_t m0, int32_t count, double res, float* d_out, cudaStream_t st);
+
 }  // namespace sdfb200

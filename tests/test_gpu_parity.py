@@ -182,3 +182,26 @@ def test_pipelined_host_path(ctx):
         got, (mx, mn) = ctx.build_from_mask(mask, res)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
         assert (mx, mn) == (wmx, wmn)
+
+
+@pytest.mark.parametrize("res", [0.01, 0.05, 0.25, 1.0, 0.0123456789, 3.7])
+def test_distance_arithmetic_matches_ieee_sqrt(ctx, res):
+    """The final pass computes (float)(sqrt((double)m) * res) with a short FP64 Newton sequence instead of sqrt.f64:
+    compare it with the host's IEEE arithmetic for EVERY squared distance a grid of <= 2048 cells per axis can hold
+    (m <= 3 * 2047^2 < 2^24), plus samples up to the not-seen sentinel, both signs."""
+    import ctypes as C
+    from sdf_tools_b200 import _capi
+    lib = _capi.load()
+    chunk = 1 << 22
+    for m0 in list(range(1, 1 << 24, chunk)) + [(1 << 25) - chunk // 2, (1 << 29), O.INF - chunk + 1]:
+        out = np.empty(chunk, np.float32)
+        assert lib.sdf_b200_debug_distance_values(ctx._h, m0, chunk, float(res), out.ctypes.data) == 0
+        m = np.arange(m0, m0 + chunk, dtype=np.int64)
+        want = (np.sqrt(m.astype(np.float64)) * res).astype(np.float32)
+        want[m >= O.INF] = np.inf
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (res, m0, int((out != want).sum()))
+    out = np.empty(chunk, np.float32)
+    assert lib.sdf_b200_debug_distance_values(ctx._h, -chunk, chunk, float(res), out.ctypes.data) == 0
+    m = np.arange(-chunk, 0, dtype=np.int64)
+    want = -(np.sqrt((-m).astype(np.float64)) * res).astype(np.float32)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))

@@ -1,0 +1,37 @@
+"""tools/ab_env.py -- A/B timing of kernel variants selected by environment knobs: each variant runs in its own process
+(the knobs are read once) on the same workloads; prints per-kernel medians and a checksum of the result."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import numpy as np, torch
+from sdf_tools_b200 import Context, synth
+res = {}
+for wl in sys.argv[1:]:
+    cfg = synth.CONFIGS[wl]; nx, ny, nz = cfg["shape"]
+    cache = "/tmp/mask_%%s.npy" %% wl
+    if os.path.exists(cache): mh = np.load(cache)
+    else: mh = synth.make_mask(wl); np.save(cache, mh)
+    m = torch.from_numpy(mh).cuda()
+    out = torch.empty((nx, ny, nz), dtype=torch.float32, device="cuda")
+    ctx = Context(0); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    acc = {}
+    for it in range(9):
+        ctx.build_device(m.data_ptr(), nx, ny, nz, cfg["res"], out.data_ptr())
+        torch.cuda.synchronize()
+        if it >= 3:
+            for k, v in ctx.last_timing().items(): acc.setdefault(k, []).append(v)
+    fin = torch.isfinite(out)
+    csum = float(out[fin].double().sum().item())
+    res[wl] = {**{k: round(float(np.median(v)), 3) for k, v in acc.items()}, "checksum": csum}
+    del m, out, ctx
+print(json.dumps(res))
+''' % ROOT
+variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band"}),
+            ("run+fp64", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "fp64"}),
+            ("run+lut", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "lut"})]
+wls = sys.argv[1:] or ["c3", "c5", "c2"]
+for name, env in variants:
+    r = subprocess.run([sys.executable, "-c", CHILD] + wls, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+    print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-600:], flush=True)
