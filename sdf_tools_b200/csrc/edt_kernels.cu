@@ -461,7 +461,7 @@ run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, 
         T.PCS = p;
     }
     const int c = threadIdx.x % LPC, b = threadIdx.x / LPC;
-    if (threadIdx.x < 2 * NW * LPC) rh_st32(T.NE + 4u * threadIdx.x, 0u);           // NE and PCS are adjacent
+    for (unsigned t = threadIdx.x; t < 2u * NW * LPC; t += blockDim.x) rh_st32(T.NE + 4u * t, 0u);   // NE and PCS are adjacent
     const int64_t col = (int64_t)blockIdx.x * LPC + c;
     const bool col_ok = col < ncols;
     int32_t* gc = g + (int64_t)blockIdx.y * outer_stride + col;
@@ -529,28 +529,22 @@ run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, 
     int32_t smax = 0, smin = 0;
     if (col_ok) {
         int32_t* dst = gc + (int64_t)base * line_stride;
-        constexpr int U = 4;                                   // results leave in groups: independent sqrt chains, batched stores
-        RH::template query<U>(T, c, b, nb, n, Pw, PCw, [&](int i0, const int32_t (&v)[U], int cnt) {
-            (void)i0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (u < cnt) {
-                    if (FINAL) {
-                        smax = max(smax, v[u]); smin = min(smin, v[u]);
-                        float f;
-                        if (USE_LUT) {
-                            const int32_t m = v[u] < 0 ? -v[u] : v[u];
-                            if (m < lut_n) f = __ldg(lut + m);
-                            else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
-                            f = __int_as_float(__float_as_int(f) | (v[u] & 0x80000000));
-                        } else f = sdf_from_signed_d2_fast(v[u], res);
-                        dst[(int64_t)u * line_stride] = __float_as_int(f);
-                    } else {
-                        dst[(int64_t)u * line_stride] = v[u];
-                    }
-                }
+        RH::query(T, c, b, nb, n, Pw, PCw, [&](int i, int32_t v) {
+            (void)i;
+            if (FINAL) {
+                smax = max(smax, v); smin = min(smin, v);
+                float f;
+                if (USE_LUT) {
+                    const int32_t m = v < 0 ? -v : v;
+                    if (m < lut_n) f = __ldg(lut + m);
+                    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+                    f = __int_as_float(__float_as_int(f) | (v & 0x80000000));
+                } else f = sdf_from_signed_d2_fast(v, res);
+                *dst = __float_as_int(f);
+            } else {
+                *dst = v;
             }
-            dst += (int64_t)U * line_stride;
+            dst += line_stride;
         });
     }
     if (dbg_on) dbg[dbg_cta * 8 + 5] = clock64();

@@ -42,8 +42,10 @@
 
 #if defined(__CUDACC__)
 #define SDF_HD __host__ __device__ __forceinline__
+#define SDF_HD_COLD __host__ __device__ __noinline__
 #else
 #define SDF_HD inline
+#define SDF_HD_COLD inline
 #endif
 
 #ifndef SDF_INF
@@ -62,7 +64,7 @@ SDF_HD int rh_hibit(uint32_t m) {             // index of the highest set bit (m
 }
 SDF_HD int rh_lobit(uint32_t m) {             // index of the lowest set bit (m != 0)
 #if defined(__CUDA_ARCH__)
-    return 31 - __clz((int)(m & (0u - m)));
+    return __ffs((int)m) - 1;
 #else
     return __builtin_ctz(m);
 #endif
@@ -255,80 +257,86 @@ struct RunHull {
         const int base = b << 5;
         int nvalid = n - base;
         nvalid = nvalid < 0 ? 0 : (nvalid > B ? B : nvalid);
-        uint32_t aw = 0, pcw = 0, pwr = 0;
+        uint32_t aw = 0, pcw = 0, pw = 0;
         if (nvalid > 0) {
             const rh_addr_t rd0 = s_addr(T, base, c);
-            int32_t vprev = (int32_t)rh_ld32_ro(b > 0 ? rd0 - STEP : rd0);          // polarity before the band
+            // polarity bits of the band (rows past the end of the line are staged zeros: masked off) and its run starts
+            {
+                uint32_t pwr = 0;
+#pragma unroll
+                for (int k = 0; k < B; ++k) pwr = rh_shift_in_sign(pwr, (int32_t)rh_ld32_ro(rd0 + (uint32_t)k * STEP));
+                pw = rh_brev(pwr) & rh_lowmask(nvalid);
+                const uint32_t prevpol = b > 0 ? (rh_ld32_ro(rd0 - STEP) >> 31) : (pw & 1u);
+                pcw = (pw ^ ((pw << 1) | prevpol)) & rh_lowmask(nvalid);
+            }
             // Chain state in band-relative lifted coordinates (i, i^2 + h): top t = (tp, tY); d = t - (vertex below t),
-            // or the sentinel d = (0, -1) that makes the test false while the chain has a single element.
+            // or the sentinel d = (0, -1) that keeps the test false while the chain has a single element.
             // bp / bY: the left boundary site of the current run when the run starts inside the band (bp = run start - 1).
-            int tp = 0, dP = 0, bp = NONE;
+            int tp = -1, dP = 0, bp = NONE;
             int32_t tY = 0, dY = -1, bY = 0;
             uint32_t botmask = 0xffffffffu;                                          // positions >= start of the current run
-            int i = 0;
-            // The chain is popped against the lifted point (i, Y); vertices that it hides are removed from `aw`.
-            auto pop_against = [&](int pi, int32_t Y) {
-                int32_t A = Y - tY;
-                int Bq = pi - tp;
+            // The chain is popped against the lifted point (pi, Y); vertices that it hides are removed from `aw`.
+            auto pop_against = [&](int pi, int32_t Y, int32_t& A, int& Bq) {
                 while (dY * Bq >= A * dP) {                                          // t on or above the chord s -> new point
                     RH_TICK(2);
-                    aw ^= 1u << tp;                                                  // (the top is a real vertex here)
+                    aw ^= 1u << tp;                                                  // (the top is a vertex here)
                     tp -= dP; tY -= dY;                                              // t <- s
-                    if (tp == bp) { dP = 0; dY = -1; }                               // the boundary site is the bottom
-                    else {
-                        const uint32_t below = aw & botmask & rh_lowmask(tp);
-                        if (below) {
-                            const int sp = rh_hibit(below);
-                            const int32_t sY = sp * sp + rh_abs((int32_t)rh_ld32_ro(rd0 + (uint32_t)sp * STEP));
-                            dP = tp - sp; dY = tY - sY;
-                        } else if (bp != NONE) { dP = tp - bp; dY = tY - bY; }
-                        else { dP = 0; dY = -1; }
-                    }
+                    const uint32_t below = tp > 0 ? (aw & botmask & rh_lowmask(tp)) : 0u;
+                    if (below) {
+                        const int sp = rh_hibit(below);
+                        const int32_t sY = sp * sp + rh_abs((int32_t)rh_ld32_ro(rd0 + (uint32_t)sp * STEP));
+                        dP = tp - sp; dY = tY - sY;
+                    } else if (bp != NONE && tp != bp) { dP = tp - bp; dY = tY - bY; }   // the boundary site is below t
+                    else { dP = 0; dY = -1; }                                        // t is the bottom of the chain
                     A = Y - tY; Bq = pi - tp;
                 }
             };
-            // phase A: nothing to do until the first run start or finite position (the chain is empty)
-            bool opened = false;
-            for (; i < nvalid; ++i) {
-                const int32_t v = (int32_t)rh_ld32_ro(rd0 + (uint32_t)i * STEP);
-                if (((v ^ vprev) < 0) || rh_abs(v) < SDF_INF) break;
-                RH_TICK(0);
-                pwr = rh_shift_in_sign(pwr, v);
-                vprev = v;
-            }
-            // phase B: the chain always has a top from the first event on
-            for (; i < nvalid; ++i) {
-                RH_TICK(0);
-                const int32_t v = (int32_t)rh_ld32_ro(rd0 + (uint32_t)i * STEP);
-                pwr = rh_shift_in_sign(pwr, v);
-                if ((v ^ vprev) < 0) {                                               // a run starts at i
+            int i = 0;
+            uint32_t rest = pcw;
+            for (;;) {
+                if (rest & (1u << i)) {                                              // a run starts at i
                     RH_TICK(3);
-                    pcw |= 1u << i;
-                    if (opened) pop_against(i, i * i);                               // close the previous run against (i, 0)
+                    rest ^= 1u << i;
+                    { int32_t A = i * i - tY; int Bq = i - tp; pop_against(i, i * i, A, Bq); }   // close the previous run against (i, 0)
                     tp = i - 1; tY = (i - 1) * (i - 1); dP = 0; dY = -1;             // open with the boundary site (i-1, 0)
                     bp = tp; bY = tY; botmask = ~rh_lowmask(i);
-                    opened = true;
                 }
-                vprev = v;
-                const int32_t h = rh_abs(v);
-                if (h < SDF_INF) {
+                const int seg_end = rest ? rh_lobit(rest) : nvalid;                  // positions [i, seg_end) belong to one run
+                // leading positions without a value: nothing to do
+                int32_t h = SDF_INF;
+                for (; i < seg_end; ++i) {
+                    RH_TICK(0);
+                    h = rh_abs((int32_t)rh_ld32_ro(rd0 + (uint32_t)i * STEP));
+                    if (h < SDF_INF) break;
+                }
+                if (i < seg_end) {
                     RH_TICK(1);
-                    const int32_t Y = i * i + h;
-                    if (!opened) { tp = i; tY = Y; opened = true; }                  // first vertex of a chain without boundary site
-                    else {
-                        pop_against(i, Y);
-                        dP = i - tp; dY = Y - tY; tp = i; tY = Y;
+                    const int32_t Y0 = i * i + h;                                    // first vertex of the run inside the band
+                    if (bp != NONE) { dP = i - bp; dY = Y0 - bY; }
+                    tp = i; tY = Y0; aw |= 1u << i;
+                    ++i;
+#pragma unroll 2
+                    for (; i < seg_end; ++i) {
+                        RH_TICK(0);
+                        const int32_t hh = rh_abs((int32_t)rh_ld32_ro(rd0 + (uint32_t)i * STEP));
+                        const int32_t Y = i * i + hh;
+                        int32_t A = Y - tY;
+                        int Bq = i - tp;
+                        if (hh < SDF_INF) {
+                            RH_TICK(1);
+                            pop_against(i, Y, A, Bq);
+                            aw |= 1u << i; dP = Bq; dY = A; tp = i; tY = Y;
+                        }
                     }
-                    aw |= 1u << i;
                 }
+                if (seg_end >= nvalid) break;
             }
             // a run that ends exactly at the end of the band is closed against its right boundary site (32, 0)
-            if (nvalid == B && base + B < n && opened) {
-                const int32_t vnext = (int32_t)rh_ld32_ro(rd0 + (uint32_t)B * STEP);
-                if ((vnext ^ vprev) < 0) pop_against(B, B * B);
+            if (nvalid == B && base + B < n) {
+                const uint32_t nextpol = rh_ld32_ro(rd0 + (uint32_t)B * STEP) >> 31;
+                if (nextpol != (pw >> 31)) { int32_t A = B * B - tY; int Bq = B - tp; pop_against(B, B * B, A, Bq); }
             }
         }
-        const uint32_t pw = nvalid ? (rh_brev(pwr) >> (32 - nvalid)) : 0u;
         stAW(T, b, c, aw);
         stPC(T, b, c, pcw);
         if (aw) rh_or32(T.NE + 4u * (uint32_t)((b >> 5) * LPC + c), 1u << (b & 31));
@@ -338,7 +346,7 @@ struct RunHull {
 
     // ------------------------------------------------------------------------------------------- phase merge
     // Clears the alive bits at positions [p0, p1) (all of them belong to dropped vertices).
-    static SDF_HD void clear_range(const RunTile& T, int c, int p0, int p1) {
+    static SDF_HD_COLD void clear_range(const RunTile& T, int c, int p0, int p1) {
         if (p1 <= p0) return;
         const int b0 = p0 >> 5, b1 = (p1 - 1) >> 5;
         for (int bb = b0; bb <= b1; ++bb) {
@@ -352,6 +360,53 @@ struct RunHull {
 
     struct Vtx { int p; int32_t Y; };     // p == NONE: no vertex
 
+    // Seam merge when no run starts inside the two groups (nor right after them): both chains are plain lists of alive
+    // vertices, walked through the band summary `ne` (bits of the left / right group) and the alive words.
+    static SDF_HD void merge_plain(const RunTile& T, int c, int sp, uint32_t neL, uint32_t neR) {
+        if (!neL || !neR) return;
+        RH_TICK(8);
+        int bL = rh_hibit(neL), bR = rh_lobit(neR);
+        neL ^= 1u << bL; neR ^= 1u << bR;
+        uint32_t wL = ldAW(T, bL, c), wR = ldAW(T, bR, c);
+        auto fetchL = [&]() -> Vtx {                                       // next vertex to the left, NONE when exhausted
+            if (!wL) {
+                if (!neL) return Vtx{NONE, 0};
+                bL = rh_hibit(neL); neL ^= 1u << bL; wL = ldAW(T, bL, c);
+            }
+            const int k = rh_hibit(wL);
+            wL ^= 1u << k;
+            const int p = 32 * bL + k;
+            return Vtx{p, p * p + rh_abs(ldS(T, p, c))};
+        };
+        auto fetchR = [&]() -> Vtx {
+            if (!wR) {
+                if (!neR) return Vtx{NONE, 0};
+                bR = rh_lobit(neR); neR ^= 1u << bR; wR = ldAW(T, bR, c);
+            }
+            const uint32_t lb = wR & (0u - wR);
+            wR ^= lb;
+            const int p = 32 * bR + rh_hibit(lb);
+            return Vtx{p, p * p + rh_abs(ldS(T, p, c))};
+        };
+        Vtx L = fetchL(), R = fetchR();
+        Vtx L2 = fetchL(), R2 = fetchR();
+        bool dropL = false, dropR = false;
+        for (;;) {
+            bool changed = false;
+            while (L2.p != NONE && rh_dominated(L2.p, L2.Y, L.p, L.Y, R.p, R.Y)) {
+                RH_TICK(5);
+                L = L2; L2 = fetchL(); dropL = true; changed = true;
+            }
+            while (R2.p != NONE && rh_dominated(L.p, L.Y, R.p, R.Y, R2.p, R2.Y)) {
+                RH_TICK(5);
+                R = R2; R2 = fetchR(); dropR = true; changed = true;
+            }
+            if (!changed) break;
+        }
+        if (dropL) clear_range(T, c, L.p + 1, sp);
+        if (dropR) clear_range(T, c, sp, R.p);
+    }
+
     // Round lv, seam at band b (b = (2j+1) << lv): joins the hulls of band groups [b-2^lv, b) and [b, b+2^lv).
     static SDF_HD void merge(const RunTile& T, int c, int b, int nb, int lv, int n) {
         const int g = 1 << lv;
@@ -362,6 +417,10 @@ struct RunHull {
         const int glo = b - g, ghi = (b + g > nb) ? nb : b + g;
         const int sp = b << 5;
         const Summ ne = ld_summ(T.NE, c), pcs = ld_summ(T.PCS, c);
+        if (NW == 1 && !(pcs.w[0] & rh_range(glo, ghi + 1))) {     // no run start in the groups or right after them
+            merge_plain(T, c, sp, ne.w[0] & rh_range(glo, b), ne.w[0] & rh_range(b, ghi));
+            return;
+        }
         // the run that crosses the seam: [a, e)
         const int a = run_start(T, c, pcs, sp - 1);
         int e;
@@ -408,11 +467,11 @@ struct RunHull {
     }
 
     // ------------------------------------------------------------------------------------------- phase query
-    // Emits out(p) for the band's positions in groups of U through `emit(i0, vals, count)`: vals[u] = out(base+i0+u),
-    // u < count (groups are computed whole; only the last group of a ragged line has count < U).
-    template <int U, typename Emit>
+    // Emits out(p) for the band's positions through `emit(i, value)`, i = position inside the band, increasing.
+    // One loop, one copy of the "next vertex" code: a position is re-evaluated after every advance, and a run start
+    // makes current == next == the run's left boundary site, so the ordinary advance fetches the run's first vertex.
+    template <typename Emit>
     static SDF_HD void query(const RunTile& T, int c, int b, int nb, int n, uint32_t pw, uint32_t pcw, Emit emit) {
-        (void)nb;
         const int base = b << 5;
         if (base >= n) return;
         int nvalid = n - base;
@@ -425,15 +484,8 @@ struct RunHull {
         // current / next hull vertex; "none" is encoded in the heights
         int cpos = base, npos = base;
         int32_t ch = SDF_INF, nh = NOSITE;
-        RIt ri;
-        ri.init_word(b, 0u, -1);
-        bool tail = false;                                                  // the run's right boundary site has been handed out
-        auto fetchN = [&]() {                                               // successor of the last vertex handed out
-            const int p = tail ? -1 : ri.next(T, c, ne);
-            if (p >= 0 && p < e) { npos = p; nh = rh_abs(ldS(T, p, c)); }
-            else if (!tail && e < n) { tail = true; npos = e; nh = 0; }
-            else { tail = true; nh = NOSITE; }
-        };
+        // vertices after `next`: alive bits `itw` of band `itb` still ahead, then later bands; tail: nothing follows
+        int itb = b; uint32_t itw = 0; bool tail = true;
         if (!(pcw & 1u)) {                                                  // position `base` continues a run from the left
             const int a = base > 0 ? run_start(T, c, pcs, base - 1) : 0;
             // L: last vertex before base, R: first vertex at / after base (boundary sites included)
@@ -441,9 +493,10 @@ struct RunHull {
             int Lp = li.next(T, c, ne); int32_t Lh = 0;
             if (Lp >= 0) Lh = rh_abs(ldS(T, Lp, c)); else if (a > 0) { Lp = a - 1; Lh = 0; } else Lp = NONE;
             int Rp; int32_t Rh = 0;
-            { const uint32_t x = myaw; int p = -1;
-              if (x) p = base + rh_lobit(x); else { const int nbnd = next_band(ne, b + 1, 32 * NW); if (nbnd >= 0) p = 32 * nbnd + rh_lobit(ldAW(T, nbnd, c)); }
-              if (p >= 0 && p < e) { Rp = p; Rh = rh_abs(ldS(T, p, c)); } else if (e < n) { Rp = e; Rh = 0; } else Rp = NONE; }
+            { int pp = -1;
+              if (myaw) pp = base + rh_lobit(myaw);
+              else { const int nbnd = next_band(ne, b + 1, 32 * NW); if (nbnd >= 0) pp = 32 * nbnd + rh_lobit(ldAW(T, nbnd, c)); }
+              if (pp >= 0 && pp < e) { Rp = pp; Rh = rh_abs(ldS(T, pp, c)); } else if (e < n) { Rp = e; Rh = 0; } else Rp = NONE; }
             bool takeR = Lp == NONE;
             if (!takeR && Rp != NONE) takeR = (base - Rp) * (base - Rp) + Rh <= (base - Lp) * (base - Lp) + Lh;
             if (takeR) {
@@ -457,38 +510,50 @@ struct RunHull {
                     if (dp * dp + Ph < dc * dc + ch) { RH_TICK(7); cpos = Pp; ch = Ph; } else break;
                 }
             }
-            // successor of cur
-            if (ch >= SDF_INF || cpos >= e) { tail = true; nh = NOSITE; }   // no vertex at all / cur is the right boundary site
-            else { ri.init(T, c, cpos + 1, n); fetchN(); }
-        }
-        for (int i0 = 0; i0 < nvalid; i0 += U) {
-            int32_t vals[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u, p = base + i;
-                if ((pcw >> i) & 1u) {                                      // a run starts at p: left boundary site (p-1, 0)
-                    const uint32_t rest = pcw & ~rh_lowmask(i + 1);
-                    e = rest ? base + rh_lobit(rest) : e_after;
-                    cpos = p - 1; ch = 0;
-                    tail = false;
-                    ri.init_word(b, myaw & ~rh_lowmask(i), n);
-                    fetchN();
-                }
-                int dc = p - cpos, dn = p - npos;
-                int32_t vc = dc * dc + ch;
-                int32_t vn = dn * dn + nh;
-                while (vn <= vc) {                                          // the next vertex takes over
-                    RH_TICK(6);
-                    cpos = npos; ch = nh; vc = vn;
-                    fetchN();
-                    dn = p - npos;
-                    vn = dn * dn + nh;
-                }
-                const int32_t best = vc < SDF_INF ? vc : SDF_INF;
-                vals[u] = ((pw >> i) & 1u) ? -best : best;
+            if (ch < SDF_INF && cpos < e) {                                 // a vertex that can have a successor
+                npos = cpos; nh = ch;                                       // next == current: the loop fetches the successor
+                tail = false;
+                itb = (cpos + 1) >> 5;                                      // (cpos >= -1)
+                itw = itb < nb ? (ldAW(T, itb, c) & ~rh_lowmask((cpos + 1) & 31)) : 0u;
             }
-            emit(i0, vals, nvalid - i0 < U ? nvalid - i0 : U);
         }
+        uint32_t rest = pcw;
+        uint32_t sgn = 0u - (pw & 1u);                                      // polarity of the current run as a mask
+        uint32_t bit = 1u;
+        const uint32_t endbit = nvalid < B ? (1u << nvalid) : 0u;           // `bit` after the last position (0 after 32 shifts)
+        int p = base;
+        do {
+            const int dc = p - cpos, dn = p - npos;
+            const int32_t vc = dc * dc + ch, vn = dn * dn + nh;
+            if ((vn <= vc) | ((rest & bit) != 0u)) {                        // rare: a run starts at p, or the next vertex takes over
+                if (rest & bit) {                                           // run start: left boundary site (p-1, 0)
+                    rest ^= bit;
+                    e = rest ? base + rh_lobit(rest) : e_after;
+                    cpos = npos = p - 1; ch = nh = 0;
+                    tail = false; itb = b; itw = myaw & (0u - bit);
+                    sgn = (pw & bit) ? 0xffffffffu : 0u;
+                    continue;
+                }
+                RH_TICK(6);
+                cpos = npos; ch = nh;                                       // advance, then fetch the successor
+                nh = NOSITE;
+                if (!tail) {
+                    if (!itw) {
+                        const int nbnd = next_band(ne, itb + 1, 32 * NW);
+                        if (nbnd >= 0) { itb = nbnd; itw = ldAW(T, nbnd, c); }
+                    }
+                    int q = e;                                              // the run's right boundary site unless a vertex comes first
+                    if (itw) { const uint32_t lb = itw & (0u - itw); q = 32 * itb + rh_hibit(lb); itw ^= lb; }
+                    if (q < e) { npos = q; nh = rh_abs(ldS(T, q, c)); }
+                    else { tail = true; if (e < n) { npos = e; nh = 0; } }
+                }
+                continue;
+            }
+            const int32_t best = vc < SDF_INF ? vc : SDF_INF;
+            emit(p - base, (int32_t)(((uint32_t)best ^ sgn) - sgn));
+            ++p;
+            bit <<= 1;
+        } while (bit != endbit);
     }
 };
 

@@ -52,7 +52,7 @@ static void pass_strided(int32_t* g, int n, int64_t line_stride, int64_t ncols, 
         for (int t : order) {
             const int b = t / LPC, c = t % LPC;
             if (c0 + c >= ncols) continue;
-            RHT::template query<4>(T, c, b, nb, n, Pw[t], PCw[t], [&](int i0, const int32_t* v, int cnt) { for (int u = 0; u < cnt; u++) outbuf[(size_t)(b * B + i0 + u) * LPC + c] = v[u]; });
+            RHT::query(T, c, b, nb, n, Pw[t], PCw[t], [&](int i, int32_t v) { outbuf[(size_t)(b * B + i) * LPC + c] = v; });
         }
         for (int c = 0; c < LPC && c0 + c < ncols; c++)
             for (int r = 0; r < n; r++) g[(int64_t)r * line_stride + c0 + c] = outbuf[(size_t)r * LPC + c];
