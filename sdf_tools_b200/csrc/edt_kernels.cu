@@ -519,12 +519,25 @@ run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, 
     if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
     __syncthreads();
     if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
-    for (int lv = 0; lv < nlevels; ++lv) {
-        // seam tasks of this round, packed onto the first threads: task = (line, seam)
-        const int seam = ((int)(threadIdx.x / LPC) * 2 + 1) << lv;
-        if (seam < nb) RH::merge(T, c, seam, nb, lv, col_ok ? n : 0);
-        __syncthreads();
+    {
+        // Seam merges.  All rounds of one line run in ONE warp (lane = seam index, 32 / P lines per warp, P = seams of round 0
+        // rounded up to a power of two), so rounds are ordered by __syncwarp and lines never wait for each other: the
+        // only CTA-wide barriers of the kernel are the one after build and the one before query.
+        int P = 1;
+        while (2 * P < nb) P <<= 1;                           // >= number of seams of round 0 (nb / 2)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int lines_per_warp = 32 / P;
+        const int mline = warp * lines_per_warp + lane / P, mj = lane % P;
+        const bool mline_ok = mline < LPC && (int64_t)blockIdx.x * LPC + mline < ncols;
+        if (warp * lines_per_warp < LPC) {                    // warp-uniform
+            for (int lv = 0; lv < nlevels; ++lv) {
+                const int seam = (2 * mj + 1) << lv;
+                if (mline_ok && seam < nb) RH::merge(T, mline, seam, nb, lv, n);
+                __syncwarp();
+            }
+        }
     }
+    __syncthreads();
     if (dbg_on) dbg[dbg_cta * 8 + 4] = clock64();
     int32_t smax = 0, smin = 0;
     if (col_ok) {
@@ -727,6 +740,9 @@ static cudaError_t launch_run_f(int32_t* g, int n, int64_t line_stride, int64_t 
                                 cudaStream_t st)
 {
 #define RUN_CFG(LPC, NBMAX, NW) return launch_run_cfg<LPC, NBMAX, NW, FINAL, USE_LUT>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st)
+    static int lpc16 = -1;                            // experiment knob: SDF_B200_LPC16=1 forces 16-line tiles below 1024 rows too
+    if (lpc16 < 0) { const char* e = getenv("SDF_B200_LPC16"); lpc16 = (e && e[0] == '1') ? 1 : 0; }
+    if (lpc16 && n <= 1024) RUN_CFG(16, 32, 1);
     if (n <= 128) RUN_CFG(32, 4, 1);
     if (n <= 256) RUN_CFG(32, 8, 1);
     if (n <= 512) RUN_CFG(32, 16, 1);

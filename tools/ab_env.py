@@ -9,10 +9,11 @@ import numpy as np, torch
 from sdf_tools_b200 import Context, synth
 res = {}
 for wl in sys.argv[1:]:
-    cfg = synth.CONFIGS[wl]; nx, ny, nz = cfg["shape"]
+    cfg = synth.CONFIGS[wl.split("@")[0]]; nx, ny, nz = cfg["shape"]
+    if "@" in wl: nx = ny = nz = int(wl.split("@")[1])
     cache = "/tmp/mask_%%s.npy" %% wl
     if os.path.exists(cache): mh = np.load(cache)
-    else: mh = synth.make_mask(wl); np.save(cache, mh)
+    else: mh = synth.make_mask(wl.split("@")[0], (nx, ny, nz)); np.save(cache, mh)
     m = torch.from_numpy(mh).cuda()
     out = torch.empty((nx, ny, nz), dtype=torch.float32, device="cuda")
     ctx = Context(0); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -30,7 +31,7 @@ print(json.dumps(res))
 ''' % ROOT
 variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band"}),
             ("run+fp64", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "fp64"}),
-            ("run+lut", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "lut"})]
+            ("run+fp64+lpc16", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "fp64", "SDF_B200_LPC16": "1"})]
 wls = sys.argv[1:] or ["c3", "c5", "c2"]
 for name, env in variants:
     r = subprocess.run([sys.executable, "-c", CHILD] + wls, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
