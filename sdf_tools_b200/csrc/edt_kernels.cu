@@ -253,8 +253,35 @@ __global__ void __launch_bounds__(256) sqrt_lut_kernel(float* __restrict__ lut, 
     if (m < n) lut[m] = (float)(sqrt((double)m) * res);
 }
 
+// (float)(sqrt((double)m) * res) for 1 <= m < 2^25, bit for bit: rsqrt seed (2^-22) -> one coupled Goldschmidt step in
+// FP64 (g ~ sqrt m, h ~ 1/(2 sqrt m) to ~2^-43) -> one Markstein correction g + (m - g*g)*h, which rounds correctly
+// (checked exhaustively for m < 2^25 with perturbed seeds in tests/test_sqrt_sequence.py and on the device in
+// tests/test_gpu_parity.py).  Ten FP64-pipe instructions instead of the ~40 of the IEEE sqrt.f64 sequence.
+__device__ __forceinline__ float sdf_dist_f32(int32_t m, double res)
+{
+    float rf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)m));
+    const double x = (double)m, r = (double)rf;
+    double gq = x * r, h = 0.5 * r;
+    const double e = fma(-gq, h, 0.5);
+    gq = fma(gq, e, gq);
+    h = fma(h, e, h);
+    const double d = fma(-gq, gq, x);
+    gq = fma(d, h, gq);
+    return (float)(gq * res);
+}
+
+__device__ __forceinline__ float sdf_from_signed_d2_fast(int32_t s, double res)
+{
+    const int32_t m = s < 0 ? -s : s;
+    float f;
+    if (m < (1 << 25)) f = sdf_dist_f32(m, res);
+    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+    return __int_as_float(__float_as_int(f) | (s & 0x80000000));
+}
+
 template <int LOGB, int LPC, int NBMAX, bool FINAL>   // NBMAX = most bands per line this instance is launched with
-__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
+__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512 && LOGB == 5) ? 3 : ((NBMAX * LPC == 256 && LOGB == 6) ? 3 : 1)) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
                                                                  int64_t line_stride, int64_t ncols,
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
@@ -372,7 +399,8 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
                 const int32_t m = v < 0 ? -v : v;
                 if (v < 0) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);
                 float f;
-                if (m < lut_n) f = __ldg(lut + m);
+                if (lut_n == 0) f = fabsf(sdf_from_signed_d2_fast(m, res));
+                else if (m < lut_n) f = __ldg(lut + m);
                 else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
                 *dst = __float_as_int(v < 0 ? -f : f);
             } else {
@@ -403,33 +431,6 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
 // (sdf_generation.hpp:246-268): (float)(sqrt((double)d2) * res) with the polarity sign, plus the extrema of the
 // signed d2 for the (max, min) pair returned at :269.
 
-// (float)(sqrt((double)m) * res) for 1 <= m < 2^25, bit for bit: rsqrt seed (2^-22) -> one coupled Goldschmidt step in
-// FP64 (g ~ sqrt m, h ~ 1/(2 sqrt m) to ~2^-43) -> one Markstein correction g + (m - g*g)*h, which rounds correctly
-// (checked exhaustively for m < 2^25 with perturbed seeds in tests/test_sqrt_sequence.py and on the device in
-// tests/test_gpu_parity.py).  Ten FP64-pipe instructions instead of the ~40 of the IEEE sqrt.f64 sequence.
-__device__ __forceinline__ float sdf_dist_f32(int32_t m, double res)
-{
-    float rf;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)m));
-    const double x = (double)m, r = (double)rf;
-    double gq = x * r, h = 0.5 * r;
-    const double e = fma(-gq, h, 0.5);
-    gq = fma(gq, e, gq);
-    h = fma(h, e, h);
-    const double d = fma(-gq, gq, x);
-    gq = fma(d, h, gq);
-    return (float)(gq * res);
-}
-
-__device__ __forceinline__ float sdf_from_signed_d2_fast(int32_t s, double res)
-{
-    const int32_t m = s < 0 ? -s : s;
-    float f;
-    if (m < (1 << 25)) f = sdf_dist_f32(m, res);
-    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
-    return __int_as_float(__float_as_int(f) | (s & 0x80000000));
-}
-
 __global__ void __launch_bounds__(256) sqrt_check_kernel(int32_t m0, int32_t count, double res, float* __restrict__ out)
 {
     const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,7 +441,7 @@ template <int LPC, int NBMAX, int NW, bool FINAL, bool USE_LUT>
 __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : ((NBMAX * LPC == 256) ? 6 : ((NBMAX * LPC == 128) ? 8 : 1)))
 run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, int64_t ncols, int64_t outer_stride,
                    double res, int* __restrict__ ext, long long* __restrict__ dbg, const float* __restrict__ lut, int lut_n,
-                   const __grid_constant__ CUtensorMap tmap, int tma_rows)
+                   const __grid_constant__ CUtensorMap tmap, int tma_rows, int merge_mode)
 {
     using RH = RunHull<LPC, NW>;
     constexpr int B = 32;
@@ -519,10 +520,16 @@ run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, 
     if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
     __syncthreads();
     if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
-    {
-        // Seam merges.  All rounds of one line run in ONE warp (lane = seam index, 32 / P lines per warp, P = seams of round 0
-        // rounded up to a power of two), so rounds are ordered by __syncwarp and lines never wait for each other: the
-        // only CTA-wide barriers of the kernel are the one after build and the one before query.
+    if (merge_mode == 0) {
+        for (int lv = 0; lv < nlevels; ++lv) {
+            // seam tasks of this round, packed onto the first threads: task = (line, seam)
+            const int seam = ((int)(threadIdx.x / LPC) * 2 + 1) << lv;
+            if (seam < nb) RH::merge(T, c, seam, nb, lv, col_ok ? n : 0);
+            __syncthreads();
+        }
+    } else {
+        // All rounds of one line run in ONE warp (lane = seam index, 32 / P lines per warp, P = seams of round 0
+        // rounded up to a power of two): rounds are ordered by __syncwarp and lines never wait for each other.
         int P = 1;
         while (2 * P < nb) P <<= 1;                           // >= number of seams of round 0 (nb / 2)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -536,8 +543,8 @@ run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, 
                 __syncwarp();
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
     if (dbg_on) dbg[dbg_cta * 8 + 4] = clock64();
     int32_t smax = 0, smin = 0;
     if (col_ok) {
@@ -729,7 +736,9 @@ static cudaError_t launch_run_cfg(int32_t* g, int n, int64_t line_stride, int64_
     dim3 grid((unsigned)((ncols + LPC - 1) / LPC), (unsigned)nouter);
     CUtensorMap tmap;
     const int tma_rows = make_tile_map(&tmap, g, n, nb, LPC, line_stride, ncols, nouter, outer_stride);
-    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, tma_rows);
+    static int mm = -1;                               // experiment knob: SDF_B200_MERGE=warp
+    if (mm < 0) { const char* e = getenv("SDF_B200_MERGE"); mm = (e && e[0] == 'w') ? 1 : 0; }
+    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, tma_rows, mm);
     return cudaGetLastError();
 }
 
@@ -743,6 +752,9 @@ static cudaError_t launch_run_f(int32_t* g, int n, int64_t line_stride, int64_t 
     static int lpc16 = -1;                            // experiment knob: SDF_B200_LPC16=1 forces 16-line tiles below 1024 rows too
     if (lpc16 < 0) { const char* e = getenv("SDF_B200_LPC16"); lpc16 = (e && e[0] == '1') ? 1 : 0; }
     if (lpc16 && n <= 1024) RUN_CFG(16, 32, 1);
+    static int lpc8 = -1;
+    if (lpc8 < 0) { const char* e = getenv("SDF_B200_LPC8"); lpc8 = (e && e[0] == '1') ? 1 : 0; }
+    if (lpc8 && n <= 1024) RUN_CFG(8, 32, 1);
     if (n <= 128) RUN_CFG(32, 4, 1);
     if (n <= 256) RUN_CFG(32, 8, 1);
     if (n <= 512) RUN_CFG(32, 16, 1);
@@ -758,6 +770,10 @@ static cudaError_t launch_band_f(int32_t* g, int n, int64_t line_stride, int64_t
                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
                                  cudaStream_t st)
 {
+    static int b64 = -1;                              // experiment knob: SDF_B200_BAND=64 -> 64-row bands
+    if (b64 < 0) { const char* e = getenv("SDF_B200_BAND"); b64 = (e && e[0] == '6') ? 1 : 0; }
+    if (b64 && n > 256 && n <= 1024) return launch_band_cfg<6, 16, 16, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
+    if (b64 && n > 1024 && n <= 2048) return launch_band_cfg<6, 16, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 256) return launch_band_cfg<5, 32, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 1024) return launch_band_cfg<5, 16, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 2048) return launch_band_cfg<5, 8, 64, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
@@ -772,7 +788,7 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
     if (hull < 0) { const char* e = getenv("SDF_B200_HULL"); hull = (e && e[0] == 'b') ? 0 : 1; }
     if (sq < 0) { const char* e = getenv("SDF_B200_SQRT"); sq = (e && e[0] == 'l') ? 0 : 1; }
     if (hull == 0)
-        return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
+        return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, sq ? 0 : lut_n, st)
                           : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
     if (!final_pass) return launch_run_f<false, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
     return sq ? launch_run_f<true, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)

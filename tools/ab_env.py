@@ -10,7 +10,9 @@ from sdf_tools_b200 import Context, synth
 res = {}
 for wl in sys.argv[1:]:
     cfg = synth.CONFIGS[wl.split("@")[0]]; nx, ny, nz = cfg["shape"]
-    if "@" in wl: nx = ny = nz = int(wl.split("@")[1])
+    if "@" in wl:
+        dims = [int(v) for v in wl.split("@")[1].split(",")]
+        nx, ny, nz = dims if len(dims) == 3 else dims * 3
     cache = "/tmp/mask_%%s.npy" %% wl
     if os.path.exists(cache): mh = np.load(cache)
     else: mh = synth.make_mask(wl.split("@")[0], (nx, ny, nz)); np.save(cache, mh)
@@ -29,9 +31,9 @@ for wl in sys.argv[1:]:
     del m, out, ctx
 print(json.dumps(res))
 ''' % ROOT
-variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band"}),
-            ("run+fp64", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "fp64"}),
-            ("run+fp64+lpc16", {"SDF_B200_HULL": "run", "SDF_B200_SQRT": "fp64", "SDF_B200_LPC16": "1"})]
+variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band", "SDF_B200_SQRT": "lut"}),
+            ("band+fp64", {"SDF_B200_HULL": "band", "SDF_B200_SQRT": "fp64"}),
+]
 wls = sys.argv[1:] or ["c3", "c5", "c2"]
 for name, env in variants:
     r = subprocess.run([sys.executable, "-c", CHILD] + wls, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
