@@ -52,6 +52,17 @@ int sdf_b200_create(sdf_b200_ctx** out, int device);
 void sdf_b200_destroy(sdf_b200_ctx* ctx);
 const char* sdf_b200_last_error(const sdf_b200_ctx* ctx); /* ctx may be NULL: error of the last create() */
 
+/* One context over SEVERAL devices of this process (one stream per device).  The host entry points
+ * (sdf_b200_build_from_mask / _from_cells) then cut the grid into z slabs, one per device, exchange the per-line slab
+ * summaries between the devices (stores into peer memory over NVLink from the summary kernel itself; NCCL all-gather
+ * when SDF_B200_EXCHANGE=nccl or without peer access; NCCL is bound at run time with dlopen("libnccl.so.2")) and run
+ * the three passes on every device concurrently -- same result, same extrema as on one device.  This is what lets
+ * CollisionMapGrid::ExtractSignedDistanceField (collision_map.hpp:680-712) scale without Python.  The device-buffer
+ * entry points of a multi-device context act on devices[0] only.  ndev == 1 is the same as sdf_b200_create. */
+int sdf_b200_create_multi(sdf_b200_ctx** out, const int* devices, int ndev);
+int sdf_b200_num_devices(const sdf_b200_ctx* ctx);          /* 1 for ordinary contexts */
+const char* sdf_b200_exchange_kind(const sdf_b200_ctx* ctx); /* "none" | "p2p" | "nccl" | "copy" */
+
 /* Stream for all launches and copies: use_own_stream != 0 selects the context's own non-blocking stream (the
  * default after create); otherwise `cuda_stream` is used as given (e.g. torch's current stream; NULL = the CUDA
  * default stream). */
@@ -113,11 +124,32 @@ int sdf_b200_slab_summary_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64
 int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
                                double resolution, const uint32_t* d_all_summaries, const int32_t* slab_widths,
                                int nranks, int rank, int keep_extrema, float* d_sdf);
+/* Steps 1 + 2 in ONE kernel, for ranks that can store to each other's memory (cudaDeviceEnablePeerAccess in one
+ * process; CUDA IPC or symmetric memory between processes): the summary word of every line of the local slab is stored
+ * straight into slot `rank` of the gather buffer of every rank -- peer_gather[k] (k < nranks, host array of device
+ * pointers valid on this device) is rank k's buffer of nranks * nx * ny words.  The caller orders the launch before the
+ * peers' sdf_b200_slab_build_device (events, or a barrier on the ranks' signal pads). */
+int sdf_b200_slab_summary_scatter_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
+                                         void* const* peer_gather, int nranks, int rank);
 /* Per-polarity maxima of the exact squared distance of the last build (0 = that polarity does not occur). */
 int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_t* out_max_filled_d2);
 /* (max, min) of sdf_generation.hpp:269 from (all-reduced) raw maxima. */
 int sdf_b200_extrema_from_raw(int32_t max_free_d2, int32_t max_filled_d2, double resolution, double* out_max,
                               double* out_min);
+
+/* Gradient field ------------------------------------------------------------------------------ */
+/* What every Python caller of the reference runs right after the build (utils_3d.py:77-90): SignedDistanceField::
+ * GetFullGradient (sdf.hpp:341-358) over GetGridAlignedGradient (sdf.hpp:432-526) -- central differences, one-sided
+ * at the faces when enable_edge_gradients, 0 along axes of one cell -- as one kernel.  d_grad / out_grad: 3 values per
+ * voxel (d/dx, d/dy, d/dz; voxel order as the field, component fastest), f64 (out_f64 != 0: bit-identical to the
+ * reference's doubles) or f32 (the f64 value rounded).  Voxels for which the reference returns an empty vector (faces
+ * with enable_edge_gradients == 0) get NaN.  The rotation by the grid's origin transform that GetGradient applies
+ * (sdf.hpp:402-430) is left to the caller (identity for axis-aligned grids, as in utils_2d / utils_3d).
+ * _host: sdf == NULL takes the field that the last host build on this context left on the device (same grid). */
+int sdf_b200_gradient_device(sdf_b200_ctx* ctx, const float* d_sdf, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                             int enable_edge_gradients, int out_f64, void* d_grad);
+int sdf_b200_gradient_host(sdf_b200_ctx* ctx, const float* sdf, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                           int enable_edge_gradients, int out_f64, void* out_grad);
 
 /* Device time of the last build on this context in milliseconds (CUDA events around the launch sequence);
  * per-kernel times in out_ms[0..3] = {pass 1 (z, binary), pass 2 (y), pass 3 (x + combine), total}. */
@@ -129,12 +161,6 @@ int sdf_b200_last_launches(const sdf_b200_ctx* ctx);
  * boundaries (start, loaded, built, barrier, merged, queried) into a device buffer; `out` (2*1024*8 values, pass 2
  * then pass 3) receives them.  enable = 0 frees the buffer.  Not for production use. */
 int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, int n);
-
-/* Diagnostics: the final pass's distance arithmetic alone.  out[i] = the f32 the build stores for a voxel whose signed
- * squared distance is m0 + i (i < count; host buffer), i.e. (float)(sqrt((double)|m|) * resolution) with the sign of
- * m (sdf_generation.hpp:254-265).  Lets tests compare the device's FP64 sequence with the host's IEEE sqrt over whole
- * ranges of m. */
-int sdf_b200_debug_distance_values(sdf_b200_ctx* ctx, int32_t m0, int32_t count, double resolution, float* out);
 
 #ifdef __cplusplus
 }

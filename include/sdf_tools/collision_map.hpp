@@ -89,14 +89,12 @@ public:
         if ((cs.x() != cs.y()) || (cs.x() != cs.z())) throw std::invalid_argument("Grid must have uniform resolution");
         if (!add_virtual_border) {
             SignedDistanceField sdf(GetOriginTransform(), frame_, cs.x(), num_x_cells_, num_y_cells_, num_z_cells_, oob_value);
-            std::vector<float> values((size_t)(num_x_cells_ * num_y_cells_ * num_z_cells_));
             double mx = 0.0, mn = 0.0;
             sdf_b200_ctx* ctx = sdf_generation::detail::Context();
             sdf_generation::detail::Check(
                 sdf_b200_build_from_cells(ctx, data_.data(), unknown_is_filled ? 1 : 0, num_x_cells_, num_y_cells_,
-                                          num_z_cells_, cs.x(), values.data(), &mx, &mn), ctx);
-            sdf.AdoptData(std::move(values));
-            return std::make_pair(sdf, std::make_pair(mx, mn));
+                                          num_z_cells_, cs.x(), sdf.GetMutableRawData().data(), &mx, &mn), ctx);
+            return std::make_pair(std::move(sdf), std::make_pair(mx, mn));     // downloaded in place, moved out
         }
         const std::function<bool(const GRID_INDEX&)> is_filled_fn = [&](const GRID_INDEX& index) {
             const auto query = GetImmutable(index);

@@ -76,15 +76,18 @@ public:
         const bool interior = x > 0 && y > 0 && z > 0 && x < num_x_cells_ - 1 && y < num_y_cells_ - 1 && z < num_z_cells_ - 1;
         if (!interior && !enable_edge_gradients) return std::vector<double>();
         const double res = GetResolution();
-        auto at = [&](int64_t a, int64_t b, int64_t c) { return (double)data_[(size_t)GetDataIndex(a, b, c)]; };
-        auto axis = [&](int64_t lo, int64_t hi, double vlo, double vhi) {
+        auto at = [&](int64_t a, int64_t b, int64_t c) { return data_[(size_t)GetDataIndex(a, b, c)]; };
+        // Bit-identical to the reference: in the interior the two neighbours are subtracted IN FLOAT and the difference
+        // is scaled in double (sdf.hpp:445-453); on the faces both values are widened to double first (:486-518).
+        auto axis = [&](int64_t lo, int64_t hi, float vlo, float vhi) {
             const double inc = (double)(hi - lo) * res;
-            return inc > 0.0 ? (vhi - vlo) * (1.0 / inc) : 0.0;
+            return inc > 0.0 ? ((double)vhi - (double)vlo) * (1.0 / inc) : 0.0;
         };
         if (interior) {
             const double inv = 1.0 / (2.0 * res);
-            return std::vector<double>{(at(x + 1, y, z) - at(x - 1, y, z)) * inv, (at(x, y + 1, z) - at(x, y - 1, z)) * inv,
-                                       (at(x, y, z + 1) - at(x, y, z - 1)) * inv};
+            return std::vector<double>{(double)(at(x + 1, y, z) - at(x - 1, y, z)) * inv,
+                                       (double)(at(x, y + 1, z) - at(x, y - 1, z)) * inv,
+                                       (double)(at(x, y, z + 1) - at(x, y, z - 1)) * inv};
         }
         const int64_t lx = std::max<int64_t>(0, x - 1), hx = std::min(num_x_cells_ - 1, x + 1);
         const int64_t ly = std::max<int64_t>(0, y - 1), hy = std::min(num_y_cells_ - 1, y + 1);

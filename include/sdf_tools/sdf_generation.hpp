@@ -14,6 +14,7 @@
 // 40-byte-per-voxel DistanceField (:19-27) is not materialised.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 #include <stdexcept>
@@ -45,9 +46,20 @@ struct ThreadContext {
 inline sdf_b200_ctx* Context() {
     static thread_local ThreadContext tc;
     if (!tc.ctx) {
-        int device = 0;
-        if (const char* e = std::getenv("SDF_B200_DEVICE")) device = std::atoi(e);
-        if (sdf_b200_create(&tc.ctx, device) != SDF_B200_OK)
+        // SDF_B200_DEVICES="0,1,2,3": one context over several GPUs (z slabs, sdf_b200_create_multi);
+        // SDF_B200_DEVICE="1": a single GPU other than device 0.
+        std::vector<int> devices;
+        if (const char* e = std::getenv("SDF_B200_DEVICES")) {
+            for (const char* p = e; *p;) {
+                char* end = nullptr;
+                const long v = std::strtol(p, &end, 10);
+                if (end == p) break;
+                devices.push_back((int)v);
+                p = (*end == ',') ? end + 1 : end;
+            }
+        }
+        if (devices.empty()) devices.push_back(std::getenv("SDF_B200_DEVICE") ? std::atoi(std::getenv("SDF_B200_DEVICE")) : 0);
+        if (sdf_b200_create_multi(&tc.ctx, devices.data(), (int)devices.size()) != SDF_B200_OK)
             throw std::runtime_error(std::string("sdf_b200: ") + sdf_b200_last_error(nullptr));
     }
     return tc.ctx;
@@ -60,15 +72,30 @@ inline void Check(int rc, sdf_b200_ctx* ctx) {
 inline std::pair<sdf_tools::SignedDistanceField, std::pair<double, double>>
 BuildFromMask(const Eigen::Isometry3d& origin, double resolution, int64_t nx, int64_t ny, int64_t nz,
               const std::vector<uint8_t>& mask, float oob_value, const std::string& frame) {
+    // The field is downloaded straight into the SignedDistanceField's own storage and the object is MOVED into the
+    // returned pair: one allocation and no host-side copy of the field.
     sdf_tools::SignedDistanceField sdf(origin, frame, resolution, nx, ny, nz, oob_value);
-    std::vector<float> values((size_t)(nx * ny * nz));
     double mx = 0.0, mn = 0.0;
     sdf_b200_ctx* ctx = Context();
-    Check(sdf_b200_build_from_mask(ctx, mask.data(), nx, ny, nz, resolution, values.data(), &mx, &mn), ctx);
-    sdf.AdoptData(std::move(values));
-    return std::make_pair(sdf, std::make_pair(mx, mn));
+    Check(sdf_b200_build_from_mask(ctx, mask.data(), nx, ny, nz, resolution, sdf.GetMutableRawData().data(), &mx, &mn), ctx);
+    return std::make_pair(std::move(sdf), std::make_pair(mx, mn));
 }
 }  // namespace detail
+
+// The whole gradient field of a finished SDF in one GPU pass: what
+// sdf.GetFullGradient([&](x,y,z,e){ return sdf.GetGridAlignedGradient(x,y,z,e); }, enable_edge_gradients) computes with
+// one std::function call per voxel (reference sdf.hpp:341-358 over :432-526), as a flat array of 3 doubles per voxel
+// in storage order.  Bit-identical to the per-voxel path; voxels for which that path returns an empty vector (faces
+// when edge gradients are disabled) hold NaN.
+inline std::vector<double> GetFullGradientArray(const sdf_tools::SignedDistanceField& sdf, const bool enable_edge_gradients = true) {
+    const int64_t nx = sdf.GetNumXCells(), ny = sdf.GetNumYCells(), nz = sdf.GetNumZCells();
+    std::vector<double> grad((size_t)(nx * ny * nz) * 3);
+    if (grad.empty()) return grad;
+    sdf_b200_ctx* ctx = detail::Context();
+    detail::Check(sdf_b200_gradient_host(ctx, sdf.GetImmutableRawData().data(), nx, ny, nz, sdf.GetResolution(),
+                                         enable_edge_gradients ? 1 : 0, 1, grad.data()), ctx);
+    return grad;
+}
 
 // Compatibility wrapper for the reference's public BuildDistanceField (:95-207): squared distance from every voxel to
 // the nearest of `points`, computed exactly on the GPU.  Throws std::runtime_error on an out-of-bounds seed (:133).

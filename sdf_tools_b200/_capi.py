@@ -18,6 +18,9 @@ SYMBOLS = [
     ("sdf_b200_version", C.c_char_p, []),
     ("sdf_b200_device_count", _int, []),
     ("sdf_b200_create", _int, [C.POINTER(_vp), _int]),
+    ("sdf_b200_create_multi", _int, [C.POINTER(_vp), C.POINTER(C.c_int), _int]),
+    ("sdf_b200_num_devices", _int, [_vp]),
+    ("sdf_b200_exchange_kind", C.c_char_p, [_vp]),
     ("sdf_b200_destroy", None, [_vp]),
     ("sdf_b200_last_error", C.c_char_p, [_vp]),
     ("sdf_b200_set_stream", _int, [_vp, _vp, _int]),
@@ -33,12 +36,14 @@ SYMBOLS = [
     ("sdf_b200_signed_d2_from_mask", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     ("sdf_b200_slab_summary_device", _int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     ("sdf_b200_slab_build_device", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _vp, C.POINTER(C.c_int32), _int, _int, _int, _vp]),
+    ("sdf_b200_slab_summary_scatter_device", _int, [_vp, _vp, _i64, _i64, _i64, C.POINTER(_vp), _int, _int]),
     ("sdf_b200_get_extrema_raw", _int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("sdf_b200_extrema_from_raw", _int, [C.c_int32, C.c_int32, _dbl, _pd, _pd]),
+    ("sdf_b200_gradient_device", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _vp]),
+    ("sdf_b200_gradient_host", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _vp]),
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),
     ("sdf_b200_last_launches", _int, [_vp]),
     ("sdf_b200_debug_phase_clocks", _int, [_vp, _int, C.POINTER(C.c_longlong), _int]),
-    ("sdf_b200_debug_distance_values", _int, [_vp, C.c_int32, C.c_int32, _dbl, _vp]),
 ]
 
 _lib = None

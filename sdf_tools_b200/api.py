@@ -22,17 +22,39 @@ class SdfB200Error(RuntimeError):
 COLLISION_CELL_DTYPE = np.dtype([("occupancy", np.float32), ("component", np.uint32)])
 
 
+def _check_out(out, shape):
+    """The C ABI writes prod(shape) floats through the pointer it is given: refuse anything else."""
+    if out is None:
+        return np.empty(shape, dtype=np.float32)
+    if not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags.c_contiguous or \
+            tuple(out.shape) != tuple(shape) or not out.flags.writeable:
+        raise ValueError(f"out must be a writeable C-contiguous float32 array of shape {tuple(shape)}")
+    return out
+
+
 class Context:
     """One device + stream + staging buffers (sdf_b200_ctx).  Not thread-safe."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: a CUDA ordinal, or a sequence of ordinals for a multi-device context (sdf_b200_create_multi: the host
+        entry points then shard the grid into z slabs over the devices; device-buffer calls act on the first one)."""
         self._lib = _capi.load()
         h = C.c_void_p()
-        rc = self._lib.sdf_b200_create(C.byref(h), int(device))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._lib.sdf_b200_create_multi(C.byref(h), devs, len(device))
+            self.devices = [int(d) for d in device]
+        else:
+            rc = self._lib.sdf_b200_create(C.byref(h), int(device))
+            self.devices = [int(device)]
         if rc != _capi.OK:
             raise SdfB200Error(rc, self._lib.sdf_b200_last_error(None).decode())
         self._h = h
-        self.device = int(device)
+        self.device = self.devices[0]
+
+    @property
+    def exchange_kind(self) -> str:
+        return self._lib.sdf_b200_exchange_kind(self._h).decode()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -63,9 +85,7 @@ class Context:
             m = (m != 0).astype(np.uint8)
         if m.ndim != 3:
             raise ValueError("mask must have shape (nx, ny, nz)")
-        if out is None:
-            out = np.empty(m.shape, dtype=np.float32)
-        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == m.shape
+        out = _check_out(out, m.shape)
         mx, mn = C.c_double(), C.c_double()
         self._check(self._lib.sdf_b200_build_from_mask(self._h, m.ctypes.data, *m.shape, float(resolution),
                                                        out.ctypes.data, C.byref(mx), C.byref(mn)))
@@ -75,10 +95,11 @@ class Context:
                          out: np.ndarray | None = None):
         """cells (nx,ny,nz) of COLLISION_CELL_DTYPE (8 B, as CollisionMapGrid stores them)."""
         c = np.ascontiguousarray(cells)
-        if c.dtype.itemsize != 8 or c.ndim != 3:
-            raise ValueError("cells must be (nx,ny,nz) of 8-byte COLLISION_CELL records")
-        if out is None:
-            out = np.empty(c.shape, dtype=np.float32)
+        if c.ndim != 3 or c.dtype.itemsize != 8 or (c.dtype.names is not None and (
+                c.dtype.names[0] != "occupancy" or c.dtype.fields["occupancy"][0] != np.float32
+                or c.dtype.fields["occupancy"][1] != 0)):
+            raise ValueError("cells must be (nx,ny,nz) of 8-byte COLLISION_CELL records {float32 occupancy; uint32 component}")
+        out = _check_out(out, c.shape)
         mx, mn = C.c_double(), C.c_double()
         self._check(self._lib.sdf_b200_build_from_cells(self._h, c.ctypes.data, int(bool(unknown_is_filled)),
                                                         *c.shape, float(resolution), out.ctypes.data,
@@ -109,6 +130,13 @@ class Context:
     def slab_summary_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, d_summary_ptr: int):
         self._check(self._lib.sdf_b200_slab_summary_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz_local,
                                                            C.c_void_p(d_summary_ptr)))
+
+    def slab_summary_scatter_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, peer_gather_ptrs, rank: int):
+        """Summary + exchange in one kernel: peer_gather_ptrs[k] = device pointer (valid on this device) of rank k's
+        gather buffer of len(peer_gather_ptrs) * nx * ny uint32 words."""
+        ptrs = (C.c_void_p * len(peer_gather_ptrs))(*[C.c_void_p(int(p)) for p in peer_gather_ptrs])
+        self._check(self._lib.sdf_b200_slab_summary_scatter_device(self._h, C.c_void_p(d_mask_ptr), nx, ny, nz_local,
+                                                                   ptrs, len(peer_gather_ptrs), int(rank)))
 
     def slab_build_device(self, d_mask_ptr: int, nx: int, ny: int, nz_local: int, resolution: float,
                           d_all_summaries_ptr: int, slab_widths, rank: int, d_sdf_ptr: int, keep_extrema: bool = False):

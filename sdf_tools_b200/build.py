@@ -10,7 +10,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsdf_b200.so")
 SOURCES = ["edt_kernels.cu", "capi.cu"]
-HEADERS = ["edt_kernels.cuh", "band_hull.cuh", "run_hull.cuh", os.path.join("..", "..", "include", "sdf_b200.h")]
+HEADERS = ["edt_kernels.cuh", "band_hull.cuh", os.path.join("..", "..", "include", "sdf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -5,10 +5,13 @@
 #include "edt_kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <limits>
+#include <vector>
 
 struct sdf_b200_ctx {
     int device = 0;
@@ -28,12 +31,22 @@ struct sdf_b200_ctx {
     void* d_in = nullptr;  size_t in_bytes = 0;     // staging for the host entry points
     void* d_mask = nullptr; size_t mask_bytes = 0;
     void* d_out = nullptr; size_t out_bytes = 0;
+    void* d_grad = nullptr; size_t grad_bytes = 0;  // gradient staging of the host entry point
+    int64_t last_dims[3] = {0, 0, 0};               // grid of the last HOST build whose field is still in d_out
     double res = 1.0;
     bool built = false;
     char err[512] = {0};
+    // ---- multi-device contexts (sdf_b200_create_multi): this context is the leader and peers[0]
+    std::vector<sdf_b200_ctx*> peers;      // empty for an ordinary context
+    bool p2p = false;                      // every pair of devices can store to each other (NVLink / NVSwitch)
+    void* d_gather = nullptr; size_t gather_bytes = 0;     // [slab][nx*ny] summaries of every slab of the current build
+    cudaEvent_t ev_summary = nullptr;      // this device's summaries have reached every peer
+    void* nccl_comm = nullptr;             // ncclComm_t of this device when the exchange goes through NCCL
+    int raw_ext[2] = {0, 0};               // extrema of the last multi-device build (already reduced over the devices)
 };
 
 static char g_create_err[512] = {0};
+static void (*nccl_destroy_comm)(void*) = nullptr;     // set when a multi-device context created NCCL communicators
 
 static int fail(sdf_b200_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess)
 {
@@ -96,9 +109,14 @@ int sdf_b200_create(sdf_b200_ctx** out, int device)
         delete ctx;
         return SDF_B200_ERR_CUDA;
     }
-    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
-    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 17; ++i) cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 17 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create: events / copy stream", e);
+        sdf_b200_destroy(ctx);
+        return SDF_B200_ERR_CUDA;
+    }
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return SDF_B200_OK;
@@ -107,8 +125,19 @@ int sdf_b200_create(sdf_b200_ctx** out, int device)
 void sdf_b200_destroy(sdf_b200_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->peers.size() > 1) {                     // a multi-device leader owns its peers (peers[0] is the leader)
+        std::vector<sdf_b200_ctx*> ps;
+        ps.swap(ctx->peers);
+        for (size_t i = 0; i < ps.size(); ++i) {
+            if (ps[i]->nccl_comm && nccl_destroy_comm) nccl_destroy_comm(ps[i]->nccl_comm);
+            ps[i]->nccl_comm = nullptr;
+            if (ps[i] != ctx) sdf_b200_destroy(ps[i]);
+        }
+    }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_summary) cudaEventDestroy(ctx->ev_summary);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 17; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -120,6 +149,7 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     if (ctx->d_in) cudaFree(ctx->d_in);
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_grad) cudaFree(ctx->d_grad);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -238,6 +268,17 @@ int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t
     if (rc) return rc;
     if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks || !slab_widths)
         return fail(ctx, SDF_B200_ERR_ARG, "bad rank / nranks / slab_widths");
+    {   // the carries make the binary pass see the WHOLE z extent: its squared distances must stay inside the 24-bit
+        // heights of the envelope passes, exactly as for an unsharded grid
+        int64_t total_nz = 0;
+        for (int r = 0; r < nranks; ++r) {
+            if (slab_widths[r] < 0) return fail(ctx, SDF_B200_ERR_ARG, "negative slab width");
+            total_nz += slab_widths[r];
+        }
+        if (total_nz > SDF_B200_MAX_AXIS)
+            return fail(ctx, SDF_B200_ERR_UNSUPPORTED, "slabs add up to a z axis longer than SDF_B200_MAX_AXIS (2048)");
+        if (slab_widths[rank] != nz_local) return fail(ctx, SDF_B200_ERR_ARG, "slab_widths[rank] != nz_local");
+    }
     const int64_t nlines = nx * ny;
     if (nlines * nz_local > 0 && (!d_mask || !d_sdf || !d_all_summaries)) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -281,6 +322,11 @@ int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_
 {
     if (!ctx) return SDF_B200_ERR_ARG;
     if (!ctx->built) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_get_extrema_raw: no finished build on this context");
+    if (ctx->peers.size() > 1) {
+        if (out_max_free_d2) *out_max_free_d2 = ctx->raw_ext[0];
+        if (out_max_filled_d2) *out_max_filled_d2 = ctx->raw_ext[1];
+        return SDF_B200_OK;
+    }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     int h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
@@ -303,6 +349,7 @@ int sdf_b200_get_extrema(sdf_b200_ctx* ctx, double* out_max, double* out_min)
 {
     if (!ctx) return SDF_B200_ERR_ARG;
     if (!ctx->built) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_get_extrema: no finished build on this context");
+    if (ctx->peers.size() > 1) return sdf_b200_extrema_from_raw(ctx->raw_ext[0], ctx->raw_ext[1], ctx->res, out_max, out_min);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     int h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
@@ -329,6 +376,174 @@ int sdf_b200_pack_cells_device(sdf_b200_ctx* ctx, const void* d_cells, int64_t n
     return SDF_B200_OK;
 }
 
+}  // extern "C"
+
+// ================================================================================= multi-device builds (one process)
+// The grid is cut into z slabs, one per device (include/sdf_b200.h, "Slab builds").  Step 2 of the protocol, the
+// exchange of the 4-byte per-line summaries, is either
+//   p2p   (default on NVLink / NVSwitch machines) the summary kernel stores each word straight into every peer's gather
+//         buffer (slab_summary_scatter_kernel) and an event per device orders the peers' builds behind it, or
+//   nccl  one ncclAllGather per device inside a group (SDF_B200_EXCHANGE=nccl, or no peer access), or
+//   copy  plain cudaMemcpyPeerAsync of the summaries (no peer access and no NCCL).
+// NCCL is bound at run time (dlopen "libnccl.so.2"): a link-time dependency would make this library load the system
+// NCCL before PyTorch's bundled, newer one in processes that import both, which breaks `import torch`.
+namespace {
+typedef int ncclResult_t;
+typedef void* ncclComm_t;
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) {
+            api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.lib, "ncclCommInitAll");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+            api.ok = api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.AllGather;
+        }
+    }
+    return api;
+}
+constexpr int NCCL_UINT32 = 3;     // ncclUint32 (nccl.h: ncclInt8 0, ncclUint8 1, ncclInt32 2, ncclUint32 3)
+
+// balanced z ranges, cut at multiples of 16 cells where possible (16-byte mask loads), as distributed.slab_ranges
+void slab_ranges(int64_t nz, int n, std::vector<int64_t>& z0, std::vector<int32_t>& w)
+{
+    const int64_t align = 16, units = nz / align;
+    w.assign(n, 0);
+    if (units >= n) {
+        for (int r = 0; r < n; ++r) w[r] = (int32_t)((units / n + (r < units % n ? 1 : 0)) * align);
+        int64_t sum = 0; for (int r = 0; r < n; ++r) sum += w[r];
+        w[n - 1] += (int32_t)(nz - sum);
+    } else {
+        for (int r = 0; r < n; ++r) w[r] = (int32_t)(nz / n + (r < nz % n ? 1 : 0));
+    }
+    z0.assign(n, 0);
+    for (int r = 1; r < n; ++r) z0[r] = z0[r - 1] + w[r - 1];
+}
+}  // namespace
+
+// Host buffers -> z slabs on the devices of a multi-device context -> host buffer.  Result and extrema are identical to
+// the single-device build: only the binary pass crosses a slab cut, and it gets its context through the carries.
+static int build_multi_host(sdf_b200_ctx* lead, const void* h_in, bool is_cells, int unknown_is_filled, int64_t nx,
+                            int64_t ny, int64_t nz, double res, float* out_sdf, double* out_max, double* out_min)
+{
+    sdf_b200_ctx* ctx = lead;                                   // for CK / fail
+    const int64_t nlines = nx * ny;
+    int n = (int)lead->peers.size();
+    if ((int64_t)n > nz) n = (int)nz;                            // never an empty slab
+    std::vector<int64_t> z0; std::vector<int32_t> w;
+    slab_ranges(nz, n, z0, w);
+    int rc;
+    // ---- upload (strided: a z slab is nlines rows of w[r] bytes in the host array) and summaries
+    std::vector<void*> gather((size_t)n);
+    for (int r = 0; r < n; ++r) {
+        sdf_b200_ctx* p = lead->peers[r];
+        CK(cudaSetDevice(p->device), "cudaSetDevice");
+        if ((rc = grow(lead, &p->d_mask, &p->mask_bytes, (size_t)(nlines * w[r])))) return rc;
+        if ((rc = grow(lead, &p->d_out, &p->out_bytes, (size_t)(nlines * w[r]) * 4))) return rc;
+        if ((rc = grow(lead, &p->d_gather, &p->gather_bytes, (size_t)n * nlines * 4))) return rc;
+        if ((rc = grow(lead, &p->d_carries, &p->carries_bytes, (size_t)nlines * 8))) return rc;
+        if (!p->d_widths) CK(cudaMalloc(&p->d_widths, 64 * sizeof(int)), "cudaMalloc(widths)");
+        gather[r] = p->d_gather;
+    }
+    const bool want_nccl = [] { const char* e = getenv("SDF_B200_EXCHANGE"); return e && e[0] == 'n'; }();
+    const bool use_nccl = n > 1 && (want_nccl || !lead->p2p) && nccl().ok && lead->nccl_comm;
+    for (int r = 0; r < n; ++r) {
+        sdf_b200_ctx* p = lead->peers[r];
+        CK(cudaSetDevice(p->device), "cudaSetDevice");
+        cudaStream_t st = p->stream;
+        if (is_cells) {
+            if ((rc = grow(lead, &p->d_in, &p->in_bytes, (size_t)(nlines * w[r]) * 8))) return rc;
+            CK(cudaMemcpy2DAsync(p->d_in, (size_t)w[r] * 8, (const char*)h_in + z0[r] * 8, (size_t)nz * 8, (size_t)w[r] * 8,
+                                 (size_t)nlines, cudaMemcpyHostToDevice, st), "H2D cells slab");
+            CK(sdfb200::launch_pack_cells(p->d_in, nlines * w[r], unknown_is_filled, (uint8_t*)p->d_mask, st), "launch pack_cells");
+        } else {
+            CK(cudaMemcpy2DAsync(p->d_mask, (size_t)w[r], (const uint8_t*)h_in + z0[r], (size_t)nz, (size_t)w[r],
+                                 (size_t)nlines, cudaMemcpyHostToDevice, st), "H2D mask slab");
+        }
+        if (n == 1) continue;
+        if (lead->p2p && !use_nccl) {
+            CK(sdfb200::launch_slab_summary_scatter((const uint8_t*)p->d_mask, w[r], nlines, gather.data(), n, r, st),
+               "launch slab_summary_scatter");
+        } else {
+            uint32_t* mine = (uint32_t*)p->d_gather + (size_t)r * nlines;
+            CK(sdfb200::launch_slab_summary((const uint8_t*)p->d_mask, w[r], nlines, mine, st), "launch slab_summary");
+            if (!use_nccl)
+                for (int k = 0; k < n; ++k)
+                    if (k != r)
+                        CK(cudaMemcpyPeerAsync((uint32_t*)lead->peers[k]->d_gather + (size_t)r * nlines, lead->peers[k]->device,
+                                               mine, p->device, (size_t)nlines * 4, st), "peer copy of the summaries");
+        }
+        if (!use_nccl) CK(cudaEventRecord(p->ev_summary, st), "event");
+    }
+    if (use_nccl) {
+        if (nccl().GroupStart() != 0) return fail(lead, SDF_B200_ERR_CUDA, "ncclGroupStart failed");
+        for (int r = 0; r < n; ++r) {
+            sdf_b200_ctx* p = lead->peers[r];
+            cudaSetDevice(p->device);
+            const ncclResult_t e = nccl().AllGather((uint32_t*)p->d_gather + (size_t)r * nlines, p->d_gather, (size_t)nlines,
+                                                    NCCL_UINT32, (ncclComm_t)p->nccl_comm, p->stream);
+            if (e != 0) { nccl().GroupEnd(); return fail(lead, SDF_B200_ERR_CUDA, nccl().GetErrorString ? nccl().GetErrorString(e) : "ncclAllGather failed"); }
+        }
+        if (nccl().GroupEnd() != 0) return fail(lead, SDF_B200_ERR_CUDA, "ncclGroupEnd failed");
+    }
+    // ---- per device: wait for every peer's summaries, resolve the carries, three passes, download
+    for (int r = 0; r < n; ++r) {
+        sdf_b200_ctx* p = lead->peers[r];
+        CK(cudaSetDevice(p->device), "cudaSetDevice");
+        cudaStream_t st = p->stream;
+        const void* carries = nullptr;
+        if (n > 1) {
+            if (!use_nccl)
+                for (int k = 0; k < n; ++k)
+                    if (k != r) CK(cudaStreamWaitEvent(st, lead->peers[k]->ev_summary, 0), "wait for peer summaries");
+            CK(cudaMemcpyAsync(p->d_widths, w.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st), "H2D widths");
+            CK(sdfb200::launch_slab_carry((const uint32_t*)p->d_gather, p->d_widths, n, r, nlines, p->d_carries, st),
+               "launch slab_carry");
+            carries = p->d_carries;
+        }
+        rc = run_passes(p, (const uint8_t*)p->d_mask, nx, ny, w[r], res, (int32_t*)p->d_out, true, carries, false);
+        if (rc) { if (p != lead) snprintf(lead->err, sizeof(lead->err), "%s", p->err); return rc; }
+        CK(cudaMemcpy2DAsync(out_sdf + z0[r], (size_t)nz * 4, p->d_out, (size_t)w[r] * 4, (size_t)w[r] * 4, (size_t)nlines,
+                             cudaMemcpyDeviceToHost, st), "D2H sdf slab");
+    }
+    int raw[2] = {0, 0}, launches = 0;
+    for (int r = 0; r < n; ++r) {
+        sdf_b200_ctx* p = lead->peers[r];
+        CK(cudaSetDevice(p->device), "cudaSetDevice");
+        int h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, p->d_ext, sizeof(h), cudaMemcpyDeviceToHost, p->stream), "copy extrema");
+        CK(cudaStreamSynchronize(p->stream), "sync");
+        raw[0] = h[0] > raw[0] ? h[0] : raw[0];
+        raw[1] = h[1] > raw[1] ? h[1] : raw[1];
+        launches += p->launches + (n > 1 ? 2 : 0) + (is_cells ? 1 : 0);
+    }
+    CK(cudaSetDevice(lead->device), "cudaSetDevice");
+    lead->raw_ext[0] = raw[0]; lead->raw_ext[1] = raw[1];
+    lead->launches = launches;
+    lead->built = true;
+    lead->res = res;
+    return sdf_b200_extrema_from_raw(raw[0], raw[1], res, out_max, out_min);
+}
+
+extern "C" {
+
 static int build_host_common(sdf_b200_ctx* ctx, const void* h_in, size_t in_bytes, bool is_cells, int unknown_is_filled,
                              int64_t nx, int64_t ny, int64_t nz, double res, float* out_sdf, double* out_max,
                              double* out_min)
@@ -353,6 +568,7 @@ static int build_host_common(sdf_b200_ctx* ctx, const void* h_in, size_t in_byte
     }
     rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, nx, ny, nz, res, (int32_t*)ctx->d_out, true);
     if (rc) return rc;
+    ctx->last_dims[0] = nx; ctx->last_dims[1] = ny; ctx->last_dims[2] = nz;
     if (is_cells && N > 0) ctx->launches++;
     if (N > 0) CK(cudaMemcpyAsync(out_sdf, ctx->d_out, (size_t)N * 4, cudaMemcpyDeviceToHost, st), "D2H sdf");
     return sdf_b200_get_extrema(ctx, out_max, out_min);
@@ -417,12 +633,15 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const uint8_t* h_mask, int64_
     CK(cudaStreamSynchronize(cs), "sync copies");
     ctx->built = true;
     ctx->res = res;
+    ctx->last_dims[0] = nx; ctx->last_dims[1] = ny; ctx->last_dims[2] = nz;
     return sdf_b200_get_extrema(ctx, out_max, out_min);
 }
 
 int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz,
                              double resolution, float* out_sdf, double* out_max, double* out_min)
 {
+    if (ctx && ctx->peers.size() > 1 && mask && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx * ny * nz > 0)
+        return build_multi_host(ctx, mask, false, 0, nx, ny, nz, resolution, out_sdf, out_max, out_min);
     if (ctx && mask && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx >= 64 && ny >= 64 &&
         nx * ny * nz >= ((int64_t)1 << 25)) {           // big enough for the copies to be worth overlapping
         CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -434,6 +653,8 @@ int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx,
 int sdf_b200_build_from_cells(sdf_b200_ctx* ctx, const void* cells, int unknown_is_filled, int64_t nx, int64_t ny,
                               int64_t nz, double resolution, float* out_sdf, double* out_max, double* out_min)
 {
+    if (ctx && ctx->peers.size() > 1 && cells && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx * ny * nz > 0)
+        return build_multi_host(ctx, cells, true, unknown_is_filled, nx, ny, nz, resolution, out_sdf, out_max, out_min);
     return build_host_common(ctx, cells, (size_t)(nx * ny * nz) * 8, true, unknown_is_filled, nx, ny, nz, resolution,
                              out_sdf, out_max, out_min);
 }
@@ -469,16 +690,128 @@ int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, i
     return SDF_B200_OK;
 }
 
-int sdf_b200_debug_distance_values(sdf_b200_ctx* ctx, int32_t m0, int32_t count, double resolution, float* out)
+int sdf_b200_slab_summary_scatter_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz_local,
+                                         void* const* peer_gather, int nranks, int rank)
 {
-    if (!ctx || count < 0 || (count > 0 && !out)) return SDF_B200_ERR_ARG;
-    if (count == 0) return SDF_B200_OK;
-    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    int rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)count * 4);
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz_local);
     if (rc) return rc;
-    CK(sdfb200::launch_sqrt_check(m0, count, resolution, (float*)ctx->d_out, ctx->stream), "launch sqrt_check");
-    CK(cudaMemcpyAsync(out, ctx->d_out, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H values");
-    CK(cudaStreamSynchronize(ctx->stream), "sync");
+    if (nranks < 1 || nranks > SDF_MAX_PEERS || rank < 0 || rank >= nranks || !peer_gather)
+        return fail(ctx, SDF_B200_ERR_ARG, "bad rank / nranks / peer_gather");
+    if (nx * ny * nz_local == 0) return SDF_B200_OK;
+    if (!d_mask) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    for (int k = 0; k < nranks; ++k) if (!peer_gather[k]) return fail(ctx, SDF_B200_ERR_ARG, "null peer gather buffer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(sdfb200::launch_slab_summary_scatter(d_mask, (int)nz_local, nx * ny, peer_gather, nranks, rank, ctx->stream),
+       "launch slab_summary_scatter");
+    return SDF_B200_OK;
+}
+
+int sdf_b200_create_multi(sdf_b200_ctx** out, const int* devices, int ndev)
+{
+    sdf_b200_ctx* ctx = nullptr;                      // for fail()
+    if (!out) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create_multi: out is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > SDF_MAX_PEERS) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create_multi: bad device list");
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create_multi: a device is listed twice");
+    std::vector<sdf_b200_ctx*> ps;
+    for (int i = 0; i < ndev; ++i) {
+        sdf_b200_ctx* p = nullptr;
+        const int rc = sdf_b200_create(&p, devices[i]);
+        if (rc != SDF_B200_OK) { for (sdf_b200_ctx* q : ps) sdf_b200_destroy(q); return rc; }
+        ps.push_back(p);
+    }
+    if (ndev == 1) { *out = ps[0]; return SDF_B200_OK; }
+    // peer access between every pair (NVLink / NVSwitch): lets the summary kernel store into the peers' gather buffers
+    bool p2p = true;
+    for (int i = 0; i < ndev && p2p; ++i)
+        for (int j = 0; j < ndev && p2p; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) { cudaGetLastError(); p2p = false; }
+        }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < ndev; ++i) {
+        if ((e = cudaSetDevice(devices[i])) != cudaSuccess) break;
+        if ((e = cudaEventCreateWithFlags(&ps[i]->ev_summary, cudaEventDisableTiming)) != cudaSuccess) break;
+        if (p2p)
+            for (int j = 0; j < ndev; ++j) {
+                if (i == j) continue;
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) p2p = false;
+                cudaGetLastError();
+            }
+    }
+    if (e != cudaSuccess) {
+        fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create_multi: events", e);
+        for (sdf_b200_ctx* q : ps) sdf_b200_destroy(q);
+        return SDF_B200_ERR_CUDA;
+    }
+    const char* ex = getenv("SDF_B200_EXCHANGE");
+    if ((!p2p || (ex && ex[0] == 'n')) && nccl().ok) {          // NCCL communicators only when they will be used
+        std::vector<ncclComm_t> comms((size_t)ndev, nullptr);
+        if (nccl().CommInitAll(comms.data(), ndev, devices) == 0) {
+            for (int i = 0; i < ndev; ++i) ps[i]->nccl_comm = comms[i];
+            nccl_destroy_comm = [](void* c) { nccl().CommDestroy((ncclComm_t)c); };
+        }
+    }
+    cudaSetDevice(devices[0]);
+    ps[0]->peers = ps;
+    ps[0]->p2p = p2p;
+    *out = ps[0];
+    return SDF_B200_OK;
+}
+
+int sdf_b200_num_devices(const sdf_b200_ctx* ctx) { return !ctx ? 0 : (ctx->peers.empty() ? 1 : (int)ctx->peers.size()); }
+
+const char* sdf_b200_exchange_kind(const sdf_b200_ctx* ctx)
+{
+    if (!ctx || ctx->peers.size() < 2) return "none";
+    const char* ex = getenv("SDF_B200_EXCHANGE");
+    if (ctx->nccl_comm && (!ctx->p2p || (ex && ex[0] == 'n'))) return "nccl";
+    return ctx->p2p ? "p2p" : "copy";
+}
+
+int sdf_b200_gradient_device(sdf_b200_ctx* ctx, const float* d_sdf, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                             int enable_edge_gradients, int out_f64, void* d_grad)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    if (nx < 0 || ny < 0 || nz < 0 || !(resolution > 0.0)) return fail(ctx, SDF_B200_ERR_ARG, "bad grid size / resolution");
+    if (nx * ny * nz == 0) return SDF_B200_OK;
+    if (!d_sdf || !d_grad) return fail(ctx, SDF_B200_ERR_ARG, "null device pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(sdfb200::launch_gradient(d_sdf, nx, ny, nz, resolution, enable_edge_gradients, out_f64, d_grad, ctx->stream),
+       "launch gradient");
+    return SDF_B200_OK;
+}
+
+int sdf_b200_gradient_host(sdf_b200_ctx* ctx, const float* sdf, int64_t nx, int64_t ny, int64_t nz, double resolution,
+                           int enable_edge_gradients, int out_f64, void* out_grad)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    if (nx < 0 || ny < 0 || nz < 0 || !(resolution > 0.0)) return fail(ctx, SDF_B200_ERR_ARG, "bad grid size / resolution");
+    const int64_t N = nx * ny * nz;
+    if (N == 0) return SDF_B200_OK;
+    if (!out_grad) return fail(ctx, SDF_B200_ERR_ARG, "null host pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (sdf) {
+        if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_out, sdf, (size_t)N * 4, cudaMemcpyHostToDevice, st), "H2D sdf");
+        ctx->last_dims[0] = nx; ctx->last_dims[1] = ny; ctx->last_dims[2] = nz;
+    } else if (!ctx->d_out || ctx->last_dims[0] != nx || ctx->last_dims[1] != ny || ctx->last_dims[2] != nz ||
+               ctx->peers.size() > 1) {
+        return fail(ctx, SDF_B200_ERR_ARG, "sdf == NULL needs the field of a host build of the same grid on this (single-device) context");
+    }
+    const size_t esz = out_f64 ? 8 : 4;
+    if ((rc = grow(ctx, &ctx->d_grad, &ctx->grad_bytes, (size_t)N * 3 * esz))) return rc;
+    CK(sdfb200::launch_gradient((const float*)ctx->d_out, nx, ny, nz, resolution, enable_edge_gradients, out_f64, ctx->d_grad, st),
+       "launch gradient");
+    CK(cudaMemcpyAsync(out_grad, ctx->d_grad, (size_t)N * 3 * esz, cudaMemcpyDeviceToHost, st), "D2H gradient");
+    CK(cudaStreamSynchronize(st), "sync");
     return SDF_B200_OK;
 }
 

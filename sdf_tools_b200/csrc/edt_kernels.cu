@@ -14,7 +14,6 @@
 // envelope passes then both run along strided axes, where 32 adjacent lines are 32 adjacent addresses.
 #include "edt_kernels.cuh"
 #include "band_hull.cuh"
-#include "run_hull.cuh"
 
 #include <cuda.h>            // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched at run time (no -lcuda)
 #include <cuda_runtime.h>
@@ -203,6 +202,43 @@ __global__ void __launch_bounds__(256) slab_summary_kernel(const uint8_t* __rest
         summary[line] = (uint32_t)lead | ((uint32_t)first << 15) | ((uint32_t)trail << 16) | ((uint32_t)last << 31);
 }
 
+// The same summary, fused with its exchange: the word of every line is stored straight into slot `rank` of the gather
+// buffer of EVERY rank (dst.p[k] = rank k's buffer, peer memory mapped over NVLink: cudaDeviceEnablePeerAccess, CUDA IPC
+// or symmetric memory), so step 2 of the protocol (the all-gather) costs no extra launch and no collective call.
+struct PeerPtrs { uint32_t* p[SDF_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) slab_summary_scatter_kernel(const uint8_t* __restrict__ mask, int nz, int64_t nlines,
+                                                                   PeerPtrs dst, int nranks, int rank)
+{
+    constexpr int LINES = 64;                         // lines per block: remote stores leave as whole 128-byte rows
+    __shared__ uint32_t words[LINES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t line0 = (int64_t)blockIdx.x * LINES;
+    for (int l = warp; l < LINES; l += 8) {
+        const int64_t line = line0 + l;
+        if (line >= nlines) break;
+        const uint8_t* mp = mask + line * nz;
+        const bool first = __ldg(mp) != 0, last = __ldg(mp + nz - 1) != 0;
+        int lead = nz, trail = nz;
+        for (int z = lane; z < nz; z += 32) {
+            const bool f = __ldg(mp + z) != 0;
+            if (f != first && z < lead) lead = z;
+            if (f != last && (nz - 1 - z) < trail) trail = nz - 1 - z;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lead = min(lead, __shfl_xor_sync(0xffffffffu, lead, o));
+            trail = min(trail, __shfl_xor_sync(0xffffffffu, trail, o));
+        }
+        if (lane == 0)
+            words[l] = (uint32_t)lead | ((uint32_t)first << 15) | ((uint32_t)trail << 16) | ((uint32_t)last << 31);
+    }
+    __syncthreads();
+    for (int k = warp; k < nranks; k += 8) {          // one warp per destination rank
+        uint32_t* out = dst.p[k] + (int64_t)rank * nlines + line0;
+        for (int l = lane; l < LINES && line0 + l < nlines; l += 32) out[l] = words[l];
+    }
+}
+
 // all[r * nlines + line] = summary of rank r; widths[r] = slab thickness of rank r.
 __global__ void __launch_bounds__(256) slab_carry_kernel(const uint32_t* __restrict__ all, const int* __restrict__ widths,
                                                          int nranks, int rank, int64_t nlines, int2* __restrict__ carries)
@@ -253,35 +289,8 @@ __global__ void __launch_bounds__(256) sqrt_lut_kernel(float* __restrict__ lut, 
     if (m < n) lut[m] = (float)(sqrt((double)m) * res);
 }
 
-// (float)(sqrt((double)m) * res) for 1 <= m < 2^25, bit for bit: rsqrt seed (2^-22) -> one coupled Goldschmidt step in
-// FP64 (g ~ sqrt m, h ~ 1/(2 sqrt m) to ~2^-43) -> one Markstein correction g + (m - g*g)*h, which rounds correctly
-// (checked exhaustively for m < 2^25 with perturbed seeds in tests/test_sqrt_sequence.py and on the device in
-// tests/test_gpu_parity.py).  Ten FP64-pipe instructions instead of the ~40 of the IEEE sqrt.f64 sequence.
-__device__ __forceinline__ float sdf_dist_f32(int32_t m, double res)
-{
-    float rf;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)m));
-    const double x = (double)m, r = (double)rf;
-    double gq = x * r, h = 0.5 * r;
-    const double e = fma(-gq, h, 0.5);
-    gq = fma(gq, e, gq);
-    h = fma(h, e, h);
-    const double d = fma(-gq, gq, x);
-    gq = fma(d, h, gq);
-    return (float)(gq * res);
-}
-
-__device__ __forceinline__ float sdf_from_signed_d2_fast(int32_t s, double res)
-{
-    const int32_t m = s < 0 ? -s : s;
-    float f;
-    if (m < (1 << 25)) f = sdf_dist_f32(m, res);
-    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
-    return __int_as_float(__float_as_int(f) | (s & 0x80000000));
-}
-
 template <int LOGB, int LPC, int NBMAX, bool FINAL>   // NBMAX = most bands per line this instance is launched with
-__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512 && LOGB == 5) ? 3 : ((NBMAX * LPC == 256 && LOGB == 6) ? 3 : 1)) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
+__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) band_strided_kernel(int32_t* __restrict__ g, int n, int nb,
                                                                  int64_t line_stride, int64_t ncols,
                                                                  int64_t outer_stride, double res, int* __restrict__ ext,
                                                                  long long* __restrict__ dbg,
@@ -399,8 +408,7 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512 && LOGB == 5)
                 const int32_t m = v < 0 ? -v : v;
                 if (v < 0) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);
                 float f;
-                if (lut_n == 0) f = fabsf(sdf_from_signed_d2_fast(m, res));
-                else if (m < lut_n) f = __ldg(lut + m);
+                if (m < lut_n) f = __ldg(lut + m);
                 else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
                 *dst = __float_as_int(v < 0 ? -f : f);
             } else {
@@ -411,173 +419,69 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512 && LOGB == 5)
     }
     if (dbg_on) dbg[dbg_cta * 8 + 5] = clock64();
     if (FINAL) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            maxpos = max(maxpos, __shfl_xor_sync(0xffffffffu, maxpos, o));
-            maxneg = max(maxneg, __shfl_xor_sync(0xffffffffu, maxneg, o));
-        }
-        if ((threadIdx.x & 31) == 0) {
+        // reduce over the lanes that exist: blockDim = nb * LPC need not be a multiple of 32 (e.g. n = 1500: 376 threads)
+        const unsigned live = __activemask();
+        maxpos = __reduce_max_sync(live, maxpos);
+        maxneg = __reduce_max_sync(live, maxneg);
+        if ((int)(threadIdx.x & 31) == __ffs((int)live) - 1) {
             if (maxpos > 0) atomicMax(ext + 0, maxpos);
             if (maxneg > 0) atomicMax(ext + 1, maxneg);
         }
     }
 }
 
-
-// ========================================================================================= K2/K3 run hull
-// Envelope pass along a strided axis with the alive-mask hulls of run_hull.cuh: tile = LPC adjacent columns x n rows,
-// staged once (TMA) and never rewritten; thread (c, b) builds and queries band b of column c, seam merges are packed
-// onto the first threads.  In place in global memory.  FINAL fuses the reference's combine loop
-// (sdf_generation.hpp:246-268): (float)(sqrt((double)d2) * res) with the polarity sign, plus the extrema of the
-// signed d2 for the (max, min) pair returned at :269.
-
-__global__ void __launch_bounds__(256) sqrt_check_kernel(int32_t m0, int32_t count, double res, float* __restrict__ out)
+// ============================================================================================== gradient field
+// Grid-aligned gradient of a finished SDF, one thread per voxel: SignedDistanceField::GetGridAlignedGradient
+// (/root/reference/include/sdf_tools/sdf.hpp:432-526) evaluated for every voxel as GetFullGradient does (:341-358).
+// Arithmetic order of the reference, so results are bit-identical to its doubles: interior voxels subtract the two
+// float neighbours IN FLOAT and scale by the double 1/(2 res) (:445-453); face voxels (enable_edge_gradients) widen both
+// values to double first and scale by 1/((hi-lo) res) (:486-518); an axis of one cell gives 0.  Voxels for which the
+// reference returns an empty vector (faces without edge gradients) get NaN in all three components.
+template <typename OUT>
+__global__ void __launch_bounds__(256) gradient_kernel(const float* __restrict__ sdf, int64_t nx, int64_t ny, int64_t nz,
+                                                       double res, double inv_twice_res, int edges, OUT* __restrict__ grad)
 {
-    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = sdf_from_signed_d2_fast(m0 + i, res);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx * ny * nz) return;
+    const int64_t z = i % nz, y = (i / nz) % ny, x = i / (nz * ny);
+    const int64_t sx = ny * nz, sy = nz;
+    double g[3];
+    const bool interior = x > 0 && y > 0 && z > 0 && x < nx - 1 && y < ny - 1 && z < nz - 1;
+    if (interior) {
+        g[0] = __dmul_rn((double)__fsub_rn(__ldg(sdf + i + sx), __ldg(sdf + i - sx)), inv_twice_res);
+        g[1] = __dmul_rn((double)__fsub_rn(__ldg(sdf + i + sy), __ldg(sdf + i - sy)), inv_twice_res);
+        g[2] = __dmul_rn((double)__fsub_rn(__ldg(sdf + i + 1), __ldg(sdf + i - 1)), inv_twice_res);
+    } else if (edges) {
+        const int64_t pos[3] = {x, y, z}, dim[3] = {nx, ny, nz}, str[3] = {sx, sy, 1};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int64_t lo = pos[a] > 0 ? pos[a] - 1 : 0, hi = pos[a] < dim[a] - 1 ? pos[a] + 1 : dim[a] - 1;
+            const double inc = __dmul_rn((double)(hi - lo), res);
+            g[a] = 0.0;
+            if (inc > 0.0) {
+                const double vhi = (double)__ldg(sdf + i + (hi - pos[a]) * str[a]);
+                const double vlo = (double)__ldg(sdf + i + (lo - pos[a]) * str[a]);
+                g[a] = __dmul_rn(__dsub_rn(vhi, vlo), __ddiv_rn(1.0, inc));
+            }
+        }
+    } else {
+        g[0] = g[1] = g[2] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    grad[3 * i + 0] = (OUT)g[0];
+    grad[3 * i + 1] = (OUT)g[1];
+    grad[3 * i + 2] = (OUT)g[2];
 }
 
-template <int LPC, int NBMAX, int NW, bool FINAL, bool USE_LUT>
-__global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : ((NBMAX * LPC == 256) ? 6 : ((NBMAX * LPC == 128) ? 8 : 1)))
-run_strided_kernel(int32_t* __restrict__ g, int n, int nb, int64_t line_stride, int64_t ncols, int64_t outer_stride,
-                   double res, int* __restrict__ ext, long long* __restrict__ dbg, const float* __restrict__ lut, int lut_n,
-                   const __grid_constant__ CUtensorMap tmap, int tma_rows, int merge_mode)
+cudaError_t launch_gradient(const float* d_sdf, int64_t nx, int64_t ny, int64_t nz, double res, int edges, int out_f64,
+                            void* d_grad, cudaStream_t st)
 {
-    using RH = RunHull<LPC, NW>;
-    constexpr int B = 32;
-    const unsigned dbg_lin = blockIdx.y * gridDim.x + blockIdx.x;
-    const unsigned dbg_stride = (gridDim.x * gridDim.y + 1023u) / 1024u;            // sample ~1024 CTAs evenly
-    const int dbg_cta = (int)(dbg_lin / dbg_stride);
-    const bool dbg_on = dbg != nullptr && threadIdx.x == 0 && (dbg_lin % dbg_stride) == 0 && dbg_cta < 1024;
-    if (dbg_on) dbg[dbg_cta * 8 + 0] = clock64();
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long tma_bar;
-    RunTile T;
-    {
-        uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw);
-        T.S = p;    p += (uint32_t)nb * B * LPC * 4;
-        T.AW = p;   p += (uint32_t)nb * LPC * 4;
-        T.PC = p;   p += (uint32_t)nb * LPC * 4;
-        T.NE = p;   p += (uint32_t)NW * LPC * 4;
-        T.PCS = p;
-    }
-    const int c = threadIdx.x % LPC, b = threadIdx.x / LPC;
-    for (unsigned t = threadIdx.x; t < 2u * NW * LPC; t += blockDim.x) rh_st32(T.NE + 4u * t, 0u);   // NE and PCS are adjacent
-    const int64_t col = (int64_t)blockIdx.x * LPC + c;
-    const bool col_ok = col < ncols;
-    int32_t* gc = g + (int64_t)blockIdx.y * outer_stride + col;
-    const int base = b << 5;
-    int nlevels = 0;
-    while ((1 << nlevels) < nb) ++nlevels;
-
-    if (tma_rows) {
-        // Tile staging by TMA: 3-D tensor-map boxes (LPC columns x tma_rows rows x 1) land in the tile's [row][line]
-        // layout; rows / columns outside the grid arrive as zeros and are never read.
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t bytes = (uint32_t)nb * B * LPC * 4u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-            const int c0 = (int)(blockIdx.x * LPC), o = (int)blockIdx.y;
-            for (int r0 = 0; r0 < nb * B; r0 += tma_rows) {
-                const uint32_t dstp = T.S + (uint32_t)r0 * (LPC * 4u);
-                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                             :: "r"(dstp), "l"(&tmap), "r"(c0), "r"(r0), "r"(o), "r"(bar) : "memory");
-            }
-        }
-        uint32_t done = 0;
-        int spins = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
-            if (!done && ++spins > (1 << 22)) __trap();       // never hang the device on a mis-programmed copy
-        }
-    } else {
-        // unaligned views: stage the band's values with plain loads
-        const rh_addr_t slot0 = RH::s_addr(T, base, c);
-        constexpr int U = 8;
-#pragma unroll
-        for (int i0 = 0; i0 < B; i0 += U) {
-            int32_t tmp[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int q = base + i0 + u;
-                tmp[u] = (col_ok && q < n) ? gc[(int64_t)q * line_stride] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) rh_st32(slot0 + (uint32_t)((i0 + u) * (LPC * 4)), (uint32_t)tmp[u]);
-        }
-        __syncthreads();
-    }
-    asm volatile("" : "+r"(T.S) :: "memory");                 // tile reads below may not move above the wait
-    if (dbg_on) dbg[dbg_cta * 8 + 1] = clock64();
-    uint32_t Pw, PCw;
-    RH::build(T, c, b, col_ok ? n : 0, Pw, PCw);
-    if (dbg_on) dbg[dbg_cta * 8 + 2] = clock64();
-    __syncthreads();
-    if (dbg_on) dbg[dbg_cta * 8 + 3] = clock64();
-    if (merge_mode == 0) {
-        for (int lv = 0; lv < nlevels; ++lv) {
-            // seam tasks of this round, packed onto the first threads: task = (line, seam)
-            const int seam = ((int)(threadIdx.x / LPC) * 2 + 1) << lv;
-            if (seam < nb) RH::merge(T, c, seam, nb, lv, col_ok ? n : 0);
-            __syncthreads();
-        }
-    } else {
-        // All rounds of one line run in ONE warp (lane = seam index, 32 / P lines per warp, P = seams of round 0
-        // rounded up to a power of two): rounds are ordered by __syncwarp and lines never wait for each other.
-        int P = 1;
-        while (2 * P < nb) P <<= 1;                           // >= number of seams of round 0 (nb / 2)
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int lines_per_warp = 32 / P;
-        const int mline = warp * lines_per_warp + lane / P, mj = lane % P;
-        const bool mline_ok = mline < LPC && (int64_t)blockIdx.x * LPC + mline < ncols;
-        if (warp * lines_per_warp < LPC) {                    // warp-uniform
-            for (int lv = 0; lv < nlevels; ++lv) {
-                const int seam = (2 * mj + 1) << lv;
-                if (mline_ok && seam < nb) RH::merge(T, mline, seam, nb, lv, n);
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-    }
-    if (dbg_on) dbg[dbg_cta * 8 + 4] = clock64();
-    int32_t smax = 0, smin = 0;
-    if (col_ok) {
-        int32_t* dst = gc + (int64_t)base * line_stride;
-        RH::query(T, c, b, nb, n, Pw, PCw, [&](int i, int32_t v) {
-            (void)i;
-            if (FINAL) {
-                smax = max(smax, v); smin = min(smin, v);
-                float f;
-                if (USE_LUT) {
-                    const int32_t m = v < 0 ? -v : v;
-                    if (m < lut_n) f = __ldg(lut + m);
-                    else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
-                    f = __int_as_float(__float_as_int(f) | (v & 0x80000000));
-                } else f = sdf_from_signed_d2_fast(v, res);
-                *dst = __float_as_int(f);
-            } else {
-                *dst = v;
-            }
-            dst += line_stride;
-        });
-    }
-    if (dbg_on) dbg[dbg_cta * 8 + 5] = clock64();
-    if (FINAL) {
-        // extrema of the signed d2 over the threads of the warp that exist (blockDim need not be a multiple of 32)
-        const unsigned live = __activemask();
-        smax = __reduce_max_sync(live, smax);
-        smin = __reduce_min_sync(live, smin);
-        if ((int)(threadIdx.x & 31) == __ffs((int)live) - 1) {
-            if (smax > 0) atomicMax(ext + 0, smax);
-            if (smin < 0) atomicMax(ext + 1, -smin);
-        }
-    }
+    const int64_t n = nx * ny * nz;
+    if (n <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const double inv2 = 1.0 / (2.0 * res);
+    if (out_f64) gradient_kernel<double><<<blocks, 256, 0, st>>>(d_sdf, nx, ny, nz, res, inv2, edges, (double*)d_grad);
+    else gradient_kernel<float><<<blocks, 256, 0, st>>>(d_sdf, nx, ny, nz, res, inv2, edges, (float*)d_grad);
+    return cudaGetLastError();
 }
 
 // ================================================================================================ launchers
@@ -624,6 +528,16 @@ cudaError_t launch_slab_summary(const uint8_t* d_mask, int nz, int64_t nlines, u
 {
     const int wpb = 8;
     slab_summary_kernel<<<(unsigned)((nlines + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_mask, nz, nlines, d_summary);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slab_summary_scatter(const uint8_t* d_mask, int nz, int64_t nlines, void* const* peer_gather, int nranks,
+                                        int rank, cudaStream_t st)
+{
+    if (nranks < 1 || nranks > SDF_MAX_PEERS) return cudaErrorInvalidValue;
+    PeerPtrs dst;
+    for (int k = 0; k < SDF_MAX_PEERS; ++k) dst.p[k] = k < nranks ? reinterpret_cast<uint32_t*>(peer_gather[k]) : nullptr;
+    slab_summary_scatter_kernel<<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(d_mask, nz, nlines, dst, nranks, rank);
     return cudaGetLastError();
 }
 
@@ -695,85 +609,13 @@ static cudaError_t launch_band_cfg(int32_t* g, int n, int64_t line_stride, int64
     return cudaGetLastError();
 }
 
-// Tensor map of one pass's view of the field: (columns, rows along the axis, outer blocks), box = LPC x rows x 1.
-// Returns the rows per box (0: the view is not TMA-addressable -> plain loads).
-static int make_tile_map(CUtensorMap* tmap, int32_t* g, int n, int nb, int lpc, int64_t line_stride, int64_t ncols,
-                         int64_t nouter, int64_t outer_stride)
-{
-    memset(tmap, 0, sizeof(*tmap));
-    static int tma_knob = -1;                         // SDF_B200_TMA=0 forces the LDG staging path
-    if (tma_knob < 0) { const char* e = getenv("SDF_B200_TMA"); tma_knob = (e && e[0] == '0') ? 0 : 1; }
-    const int64_t ostride = nouter > 1 ? outer_stride : line_stride * (int64_t)n;
-    if (!(tma_knob && tensor_map_encoder() && (line_stride % 4) == 0 && (ostride % 4) == 0 &&
-          (reinterpret_cast<uintptr_t>(g) & 15) == 0))
-        return 0;
-    const cuuint64_t gdim[3] = {(cuuint64_t)ncols, (cuuint64_t)n, (cuuint64_t)nouter};
-    const cuuint64_t gstr[2] = {(cuuint64_t)line_stride * 4u, (cuuint64_t)ostride * 4u};
-    int bpb = 1;                                      // bands per box: the largest divisor of nb with <= 256 rows
-    for (int d = 2; d * 32 <= 256; ++d) if (nb % d == 0) bpb = d;
-    const int rows = bpb * 32;
-    const cuuint32_t box[3] = {(cuuint32_t)lpc, (cuuint32_t)rows, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUresult r = tensor_map_encoder()(tmap, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, g, gdim, gstr, box, estr,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? rows : 0;
-}
-
-template <int LPC, int NBMAX, int NW, bool FINAL, bool USE_LUT>
-static cudaError_t launch_run_cfg(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
-                                  cudaStream_t st)
-{
-    const int nb = (n + 31) / 32;
-    if (nb > NBMAX) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)nb * 32 * LPC * 4 + (size_t)nb * LPC * 8 + (size_t)NW * LPC * 8;
-    auto kern = run_strided_kernel<LPC, NBMAX, NW, FINAL, USE_LUT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    dim3 grid((unsigned)((ncols + LPC - 1) / LPC), (unsigned)nouter);
-    CUtensorMap tmap;
-    const int tma_rows = make_tile_map(&tmap, g, n, nb, LPC, line_stride, ncols, nouter, outer_stride);
-    static int mm = -1;                               // experiment knob: SDF_B200_MERGE=warp
-    if (mm < 0) { const char* e = getenv("SDF_B200_MERGE"); mm = (e && e[0] == 'w') ? 1 : 0; }
-    kern<<<grid, nb * LPC, smem, st>>>(g, n, nb, line_stride, ncols, outer_stride, res, ext, dbg, lut, lut_n, tmap, tma_rows, mm);
-    return cudaGetLastError();
-}
-
-// Tile shapes: lines per CTA chosen so that a CTA has <= 512 threads and <= 64 KB of tile (3 CTAs per SM at the large sizes).
-template <bool FINAL, bool USE_LUT>
-static cudaError_t launch_run_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
-                                int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
-                                cudaStream_t st)
-{
-#define RUN_CFG(LPC, NBMAX, NW) return launch_run_cfg<LPC, NBMAX, NW, FINAL, USE_LUT>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st)
-    static int lpc16 = -1;                            // experiment knob: SDF_B200_LPC16=1 forces 16-line tiles below 1024 rows too
-    if (lpc16 < 0) { const char* e = getenv("SDF_B200_LPC16"); lpc16 = (e && e[0] == '1') ? 1 : 0; }
-    if (lpc16 && n <= 1024) RUN_CFG(16, 32, 1);
-    static int lpc8 = -1;
-    if (lpc8 < 0) { const char* e = getenv("SDF_B200_LPC8"); lpc8 = (e && e[0] == '1') ? 1 : 0; }
-    if (lpc8 && n <= 1024) RUN_CFG(8, 32, 1);
-    if (n <= 128) RUN_CFG(32, 4, 1);
-    if (n <= 256) RUN_CFG(32, 8, 1);
-    if (n <= 512) RUN_CFG(32, 16, 1);
-    if (n <= 1024) RUN_CFG(16, 32, 1);
-    if (n <= 2048) RUN_CFG(8, 64, 2);
-#undef RUN_CFG
-    return cudaErrorInvalidValue;
-}
-
-// Tile shapes (old band kernel): bands of 32 rows everywhere; lines per CTA chosen so a CTA has <= 512 threads and ~64 KB of stacks
+// Tile shapes: bands of 32 rows everywhere; lines per CTA chosen so a CTA has <= 512 threads and ~64 KB of stacks
+// (3 CTAs per SM): n <= 256 -> 32 lines x <= 8 bands, n <= 1024 -> 16 lines x <= 32 bands, n <= 2048 -> 8 lines x <= 64 bands.
 template <bool FINAL>
 static cudaError_t launch_band_f(int32_t* g, int n, int64_t line_stride, int64_t ncols, int64_t nouter,
                                  int64_t outer_stride, double res, int* ext, long long* dbg, const float* lut, int lut_n,
                                  cudaStream_t st)
 {
-    static int b64 = -1;                              // experiment knob: SDF_B200_BAND=64 -> 64-row bands
-    if (b64 < 0) { const char* e = getenv("SDF_B200_BAND"); b64 = (e && e[0] == '6') ? 1 : 0; }
-    if (b64 && n > 256 && n <= 1024) return launch_band_cfg<6, 16, 16, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
-    if (b64 && n > 1024 && n <= 2048) return launch_band_cfg<6, 16, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 256) return launch_band_cfg<5, 32, 8, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 1024) return launch_band_cfg<5, 16, 32, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
     if (n <= 2048) return launch_band_cfg<5, 8, 64, FINAL>(g, n, line_stride, ncols, nouter, outer_stride, res, ext, dbg, lut, lut_n, st);
@@ -784,22 +626,8 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
                                 int64_t outer_stride, bool final_pass, double res, int* d_ext, long long* d_dbg,
                                 const float* d_lut, int lut_n, cudaStream_t st)
 {
-    static int hull = -1, sq = -1;                    // experiment knobs: SDF_B200_HULL=band|run, SDF_B200_SQRT=lut|fp64
-    if (hull < 0) { const char* e = getenv("SDF_B200_HULL"); hull = (e && e[0] == 'b') ? 0 : 1; }
-    if (sq < 0) { const char* e = getenv("SDF_B200_SQRT"); sq = (e && e[0] == 'l') ? 0 : 1; }
-    if (hull == 0)
-        return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, sq ? 0 : lut_n, st)
-                          : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
-    if (!final_pass) return launch_run_f<false, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
-    return sq ? launch_run_f<true, false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
-              : launch_run_f<true, true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
-}
-
-cudaError_t launch_sqrt_check(int32_t m0, int32_t count, double res, float* d_out, cudaStream_t st)
-{
-    if (count <= 0) return cudaSuccess;
-    sqrt_check_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(m0, count, res, d_out);
-    return cudaGetLastError();
+    return final_pass ? launch_band_f<true>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st)
+                      : launch_band_f<false>(g, n, line_stride, ncols, nouter, outer_stride, res, d_ext, d_dbg, d_lut, lut_n, st);
 }
 
 }  // namespace sdfb200

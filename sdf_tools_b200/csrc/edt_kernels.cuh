@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define SDF_MAX_PEERS 32   // ranks of one slab build whose gather buffers a single launch can store to
+
 namespace sdfb200 {
 
 // K0: COLLISION_CELL[n] (8 B each) -> uint8 mask, rule of collision_map.hpp:686-709
@@ -17,6 +19,9 @@ cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64
 // Slab (multi-GPU) support for the binary pass: per-line 4-byte summary of one slab, and the resolution of one
 // rank's carries from the all-gathered summaries of every rank (d_all[r*nlines + line], d_widths[r]).
 cudaError_t launch_slab_summary(const uint8_t* d_mask, int nz, int64_t nlines, uint32_t* d_summary, cudaStream_t st);
+// summary + exchange in one kernel: peer_gather[k] = gather buffer of rank k (device pointers valid on this device)
+cudaError_t launch_slab_summary_scatter(const uint8_t* d_mask, int nz, int64_t nlines, void* const* peer_gather, int nranks,
+                                        int rank, cudaStream_t st);
 cudaError_t launch_slab_carry(const uint32_t* d_all, const int* d_widths, int nranks, int rank, int64_t nlines,
                               void* d_carries, cudaStream_t st);
 
@@ -30,7 +35,8 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
 // d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution
 cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st);   // d_dbg: optional 2 x 1024 x 8 phase clocks (diagnostics), or NULL
 
-// out[i] = the final pass's distance value for signed d2 = m0 + i (diagnostics / tests)
-cudaError_t launch_sqrt_check(int32_t m0, int32_t count, double res, float* d_out, cudaStream_t st);
+// Grid-aligned gradient field of an f32 SDF (reference sdf.hpp:341-358 + :432-526): d_grad = 3 values per voxel, f64 or f32
+cudaError_t launch_gradient(const float* d_sdf, int64_t nx, int64_t ny, int64_t nz, double res, int edges, int out_f64,
+                            void* d_grad, cudaStream_t st);
 
 }  // namespace sdfb200

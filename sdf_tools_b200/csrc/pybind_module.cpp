@@ -58,6 +58,19 @@ PYBIND11_MODULE(pysdf_tools, m) {
             return a;
         })
         .def("GetFullGradient", &SignedDistanceField::GetFullGradient)
+        .def("GetFullGradientArray",                            // (nx, ny, nz, 3) float64, one GPU pass
+             [](const SignedDistanceField& s, bool edges) {
+                 py::array_t<double> a({s.GetNumXCells(), s.GetNumYCells(), s.GetNumZCells(), (int64_t)3});
+                 if (a.size() > 0) {
+                     sdf_b200_ctx* ctx = sdf_generation::detail::Context();
+                     sdf_generation::detail::Check(
+                         sdf_b200_gradient_host(ctx, s.GetImmutableRawData().data(), s.GetNumXCells(), s.GetNumYCells(),
+                                                s.GetNumZCells(), s.GetResolution(), edges ? 1 : 0, 1, a.mutable_data()), ctx);
+                 }
+                 return a;
+             },
+             "grid-aligned gradient of every voxel, bit-identical to GetGridAlignedGradient per voxel",
+             py::arg("enable_edge_gradients") = true)
         .def("GetResolution", &SignedDistanceField::GetResolution)
         .def("GetFrame", &SignedDistanceField::GetFrame)
         .def("GetGradient",

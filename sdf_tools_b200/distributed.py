@@ -27,6 +27,8 @@ def slab_ranges(nz: int, nranks: int, align: int = 16):
     """Balanced z ranges [z0, z1) per rank, cut at multiples of `align` where possible (16-byte mask loads)."""
     if nranks < 1:
         raise ValueError("nranks must be >= 1")
+    if nranks > nz:
+        raise ValueError(f"cannot cut {nz} z planes into {nranks} non-empty slabs")
     units = nz // align
     if units >= nranks:
         base, extra = divmod(units, nranks)
@@ -135,6 +137,8 @@ class SlabBuilder:
             parts -= 1
         self.parts = parts
         self.nslabs = world * parts
+        if self.nz > 2048:
+            raise ValueError("the z axis (all slabs together) is limited to SDF_B200_MAX_AXIS = 2048 cells")
         self.ranges = slab_ranges(self.nz, self.nslabs)
         self.widths = [b - a for a, b in self.ranges]
         self.slab_ids = [p * world + rank for p in range(parts)]          # global slab index of each local part
@@ -146,6 +150,27 @@ class SlabBuilder:
         nl = self.nx * self.ny
         self.summary = torch.empty(parts * nl, dtype=torch.int32, device=dev)
         self.all_summaries = torch.empty(self.nslabs * nl, dtype=torch.int32, device=dev)
+        # Exchange of the summaries: "p2p" = the summary kernel stores into every rank's gather buffer (symmetric memory
+        # over NVLink, one signal-pad barrier); "nccl" = all_gather_into_tensor.  SDF_B200_EXCHANGE=nccl|p2p forces one.
+        self.exchange = "nccl" if world > 1 else "none"
+        self._symm = None
+        want = os.environ.get("SDF_B200_EXCHANGE", "p2p")
+        if world > 1 and parts == 1 and want != "nccl":
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                # two gather buffers used alternately: build i+1 may store while a slow peer still reads build i
+                buf = symm_mem.empty(2 * self.nslabs * nl, dtype=torch.int32, device=dev)
+                hdl = symm_mem.rendezvous(buf, grp)
+                self._symm_buf = buf
+                self._symm = hdl
+                self._peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+                self._parity = 0
+                self.exchange = "p2p"
+            except Exception as e:               # no symmetric memory on this build / topology: NCCL all-gather
+                self._symm = None
+                self._symm_error = repr(e)
 
     def alloc_outputs(self):
         torch = self.torch
@@ -162,6 +187,21 @@ class SlabBuilder:
         ctx = self.ctx
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         nl = self.nx * self.ny
+        if self._symm is not None:
+            # summary + exchange in one kernel over peer memory; the barriers order (previous build's readers) ->
+            # (stores of every rank) -> (this build's readers) on the current stream
+            # One signal-pad barrier per build: it orders (stores of every rank into buffer `parity`) before (the
+            # carry kernels that read it).  The buffer of build i is rewritten by build i+2, i.e. after the barrier of
+            # build i+1, which no rank passes before its own build i has finished reading.
+            off = self._parity * self.nslabs * nl * 4
+            self._parity ^= 1
+            ctx.slab_summary_scatter_device(d_masks[0].data_ptr(), self.nx, self.ny, self.widths[self.rank],
+                                            [p + off for p in self._peer_ptrs], self.rank)
+            self._symm.barrier(channel=0)
+            self.all_summaries = self._symm_buf[off // 4: off // 4 + self.nslabs * nl]
+            ctx.slab_build_device(d_masks[0].data_ptr(), self.nx, self.ny, self.widths[self.rank], resolution,
+                                  self._symm_buf.data_ptr() + off, self.widths, self.rank, d_sdfs[0].data_ptr())
+            return d_sdfs
         for p, m in enumerate(d_masks):
             w = self.widths[self.slab_ids[p]]
             ctx.slab_summary_device(m.data_ptr(), self.nx, self.ny, w, self.summary[p * nl:].data_ptr())

@@ -1,7 +1,7 @@
 """sdf_tools_b200/utils_2d.py -- 2-D convenience wrapper with the call signature of the reference's
 ``sdf_tools.utils_2d.compute_sdf_and_gradient`` (src/sdf_tools/utils_2d.py:6-55), implemented on bulk arrays:
-one SetOccupancy call instead of a Python SetValue loop, one memcpy instead of a list copy, numpy gradients instead
-of a Python callback per voxel."""
+one SetOccupancy call instead of a Python SetValue loop, one memcpy instead of a list copy, one GPU gradient pass
+instead of a Python callback per voxel."""
 from __future__ import annotations
 
 import numpy as np
@@ -9,14 +9,12 @@ import numpy as np
 from . import pysdf_tools
 
 
-def _gradient(sdf: np.ndarray, res: float) -> np.ndarray:
-    """Per-axis gradient with the reference's edge rule (SignedDistanceField.GetGradient(.., True), sdf.hpp:432-526):
-    central differences inside, one-sided at the faces, 0 along axes of length 1."""
-    comps = []
-    for ax in range(sdf.ndim):
-        comps.append(np.gradient(sdf.astype(np.float64), res, axis=ax, edge_order=1) if sdf.shape[ax] > 1
-                     else np.zeros(sdf.shape, np.float64))
-    return np.stack(comps, axis=-1)
+def _gradient(sdf_grid) -> np.ndarray:
+    """(nx, ny, nz, 3) float64 gradient field of a pysdf_tools.SignedDistanceField with the reference's edge rule
+    (SignedDistanceField.GetGradient(.., True), sdf.hpp:432-526): central differences inside, one-sided at the
+    faces, 0 along axes of length 1 -- computed by the GPU kernel behind GetFullGradientArray, bit-identical to the
+    reference's per-voxel GetFullGradient loop (utils_2d.py:44-47)."""
+    return sdf_grid.GetFullGradientArray(True)
 
 
 def compute_sdf_and_gradient(grid_world, sdf_resolution, sdf_origin, frame="world"):
@@ -30,5 +28,5 @@ def compute_sdf_and_gradient(grid_world, sdf_resolution, sdf_origin, frame="worl
     grid.SetOccupancy(np.ascontiguousarray((grid_world == 1).T[:, :, None], dtype=np.float32))
     sdf_grid, _extrema = grid.ExtractSignedDistanceField(oob.occupancy, False, False)
     sdf_xy = sdf_grid.numpy()[:, :, 0]                                   # (x, y)
-    grad_xy = _gradient(sdf_xy, sdf_grid.GetResolution())               # (x, y, 2): d/dx, d/dy
+    grad_xy = _gradient(sdf_grid)[:, :, 0, 0:2]                          # (x, y, 2): d/dx, d/dy ("remove the z gradient")
     return sdf_xy.T.astype(np.float32), np.transpose(grad_xy, (1, 0, 2)).astype(np.float32)

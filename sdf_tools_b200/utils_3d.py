@@ -29,10 +29,10 @@ def compute_sdf_and_gradient(env, res, origin_point):
     """env [y, x, z] of 0/1 -> (sdf [y, x, z] float32, gradient [y, x, z, 3] float32 with components d/dx, d/dy, d/dz)."""
     sdf = compute_sdf(env, res, origin_point)
     xyz = sdf.numpy()
-    grad = _gradient(xyz, sdf.GetResolution())
+    grad = _gradient(sdf)
     return np.transpose(xyz, (1, 0, 2)).astype(np.float32), np.transpose(grad, (1, 0, 2, 3)).astype(np.float32)
 
 
 def get_gradient(sdf, dtype=np.float64):
     """Full gradient field (nx, ny, nz, 3) of a pysdf_tools.SignedDistanceField, edge gradients enabled."""
-    return _gradient(sdf.numpy(), sdf.GetResolution()).astype(dtype)
+    return _gradient(sdf).astype(dtype)

@@ -125,3 +125,51 @@ def test_build_distance_field_compat(P):
     assert np.array_equal(d2, want)
     with pytest.raises(RuntimeError):
         P.BuildDistanceFieldD2(4, 4, 4, [(9, 0, 0)])          # out-of-bounds seed (:133)
+
+
+def _gradient_restated(sdf: np.ndarray, res: float, edges: bool) -> np.ndarray:
+    """GetGridAlignedGradient (reference sdf.hpp:432-526) line by line in numpy, with its arithmetic types: interior
+    voxels subtract the float neighbours IN FLOAT and multiply by the double 1/(2 res) (:445-453); face voxels widen to
+    double first and multiply by 1/((hi-lo) res) (:486-518); no gradient (NaN here) on faces without edge gradients."""
+    nx, ny, nz = sdf.shape
+    out = np.full(sdf.shape + (3,), np.nan, np.float64)
+    inv2 = 1.0 / (2.0 * res)
+    X, Y, Z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    interior = (X > 0) & (Y > 0) & (Z > 0) & (X < nx - 1) & (Y < ny - 1) & (Z < nz - 1)
+    for a, (I, n) in enumerate(((X, nx), (Y, ny), (Z, nz))):
+        lo, hi = np.maximum(I - 1, 0), np.minimum(I + 1, n - 1)
+        idx_lo, idx_hi = [X, Y, Z], [X, Y, Z]
+        idx_lo[a], idx_hi[a] = lo, hi
+        vlo, vhi = sdf[tuple(idx_lo)], sdf[tuple(idx_hi)]                      # float32
+        with np.errstate(invalid="ignore", divide="ignore"):
+            g_int = (vhi - vlo).astype(np.float64) * inv2                       # float subtraction, then double
+            inc = (hi - lo).astype(np.float64) * res
+            g_edge = np.where(inc > 0.0, (vhi.astype(np.float64) - vlo.astype(np.float64)) * (1.0 / np.where(inc > 0, inc, 1.0)), 0.0)
+        out[..., a] = np.where(interior, g_int, g_edge if edges else np.nan)
+    return out
+
+
+@pytest.mark.parametrize("shape", [(9, 7, 5), (20, 40, 1), (1, 1, 6), (3, 3, 3), (33, 17, 65)])
+def test_device_gradient_is_bit_identical(P, shape):
+    """the GPU gradient field == GetGridAlignedGradient of every voxel, bit for bit."""
+    mask = synth.iid(shape, 0.1, 31)
+    tf = P.Isometry3d([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    grid = P.CollisionMapGrid(tf, "w", 0.037, *shape, P.COLLISION_CELL(0.0))
+    grid.SetOccupancy(mask.astype(np.float32))
+    sdf = grid.ExtractSignedDistanceField(0.0, False, False)[0]
+    field = sdf.numpy()
+    for edges in (True, False):
+        got = sdf.GetFullGradientArray(edges)
+        want = _gradient_restated(field, sdf.GetResolution(), edges)
+        assert got.shape == shape + (3,)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or np.array_equal(np.isnan(got), np.isnan(want)) and \
+            np.array_equal(got[~np.isnan(got)].view(np.uint64), want[~np.isnan(want)].view(np.uint64))
+        # and against the C++ per-voxel path (host loop with the reference's float / double order)
+        rng = np.random.default_rng(1)
+        for _ in range(60):
+            x, y, z = (int(rng.integers(0, n)) for n in shape)
+            g = sdf.GetGradient(x, y, z, edges)
+            if len(g) == 0:
+                assert np.isnan(got[x, y, z]).all()
+            else:
+                assert np.array_equal(np.asarray(g, np.float64).view(np.uint64), got[x, y, z].view(np.uint64))

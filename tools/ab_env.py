@@ -32,7 +32,7 @@ for wl in sys.argv[1:]:
 print(json.dumps(res))
 ''' % ROOT
 variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band", "SDF_B200_SQRT": "lut"}),
-            ("band+fp64", {"SDF_B200_HULL": "band", "SDF_B200_SQRT": "fp64"}),
+
 ]
 wls = sys.argv[1:] or ["c3", "c5", "c2"]
 for name, env in variants:
