@@ -153,17 +153,22 @@ def _gradient_restated(sdf: np.ndarray, res: float, edges: bool) -> np.ndarray:
 def test_device_gradient_is_bit_identical(P, shape):
     """the GPU gradient field == GetGridAlignedGradient of every voxel, bit for bit."""
     mask = synth.iid(shape, 0.1, 31)
+    mask.reshape(-1)[mask.size // 2] = 1                  # never an all-free grid (its SDF is +inf everywhere)
     tf = P.Isometry3d([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
     grid = P.CollisionMapGrid(tf, "w", 0.037, *shape, P.COLLISION_CELL(0.0))
     grid.SetOccupancy(mask.astype(np.float32))
     sdf = grid.ExtractSignedDistanceField(0.0, False, False)[0]
     field = sdf.numpy()
+    def same(a, b):                                  # bit-identical, any NaN equal to any NaN (payloads are not specified)
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        na, nb = np.isnan(a), np.isnan(b)
+        return np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint64), b[~nb].view(np.uint64))
+
     for edges in (True, False):
         got = sdf.GetFullGradientArray(edges)
         want = _gradient_restated(field, sdf.GetResolution(), edges)
         assert got.shape == shape + (3,)
-        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or np.array_equal(np.isnan(got), np.isnan(want)) and \
-            np.array_equal(got[~np.isnan(got)].view(np.uint64), want[~np.isnan(want)].view(np.uint64))
+        assert same(got, want)
         # and against the C++ per-voxel path (host loop with the reference's float / double order)
         rng = np.random.default_rng(1)
         for _ in range(60):
@@ -172,4 +177,4 @@ def test_device_gradient_is_bit_identical(P, shape):
             if len(g) == 0:
                 assert np.isnan(got[x, y, z]).all()
             else:
-                assert np.array_equal(np.asarray(g, np.float64).view(np.uint64), got[x, y, z].view(np.uint64))
+                assert same(g, got[x, y, z])
