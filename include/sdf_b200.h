@@ -137,6 +137,32 @@ int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_
 int sdf_b200_extrema_from_raw(int32_t max_free_d2, int32_t max_filled_d2, double resolution, double* out_max,
                               double* out_min);
 
+/* add_virtual_border (reference sdf_generation.hpp:287-419) ------------------------------------- */
+/* Every axis longer than one cell grows by a one-cell shell; the free-space values come from a build whose shell is
+ * FILLED, the inside values from a build whose shell is FREE, selected per real voxel as
+ * a >= 0 ? a : (b <= -0 ? b : 0) (:381-409); extrema = (max of the first build, min of the second) (:412-413).  All of it
+ * on the device: one upload of the inner mask(s), two builds on the padded grid, one download of nx*ny*nz floats.
+ * mask_free / mask_filled: the is_filled predicate as evaluated during the reference's first / second extraction (it
+ * calls the predicate once per voxel in each, :381-382); the same pointer twice for a pure predicate. */
+int sdf_b200_build_with_border(sdf_b200_ctx* ctx, const uint8_t* mask_free, const uint8_t* mask_filled, int64_t nx, int64_t ny,
+                               int64_t nz, double resolution, float* out_sdf, double* out_max, double* out_min);
+
+/* Batched object SDFs --------------------------------------------------------------------------- */
+/* TaggedObjectCollisionMapGrid callers (reference tagged_object_collision_map.hpp): MakeObjectSDFs (:875-915) runs one
+ * full ExtractSignedDistanceField(objects_to_use = {id}) (:813-856) per object id, ExtractFreeAndNamedObjects... (:730-811)
+ * two more.  Here the tagged cells -- nx*ny*nz x {float occupancy; u32 component; u32 object_id; u32 convex_segment},
+ * 16 bytes (:22-43) -- are uploaded once, one pass over them answers up to 8 queries (one mask bit each) and the builds
+ * run back to back while the previous result downloads.  Query k fills out_sdfs[k*N .. (k+1)*N) (N = nx*ny*nz) and
+ * out_max[k] / out_min[k] with exactly what the reference's call for that predicate returns (exact EDT):
+ *   kind 0  filled cells whose object_id == object_id        (objects_to_use = {object_id})
+ *   kind 1  every filled cell                                  (objects_to_use empty; the "free" field of :733-753)
+ *   kind 2  filled cells of named objects, object_id > 0       (the "named objects" field of :755-778)
+ * filled = occupancy > 0.5, or == 0.5 when unknown_is_filled. */
+typedef struct { uint32_t object_id; uint32_t kind; } sdf_b200_object_query;
+int sdf_b200_build_object_sdfs(sdf_b200_ctx* ctx, const void* tagged_cells, int64_t nx, int64_t ny, int64_t nz,
+                               double resolution, int unknown_is_filled, const sdf_b200_object_query* queries, int nqueries,
+                               float* out_sdfs, double* out_max, double* out_min);
+
 /* Gradient field ------------------------------------------------------------------------------ */
 /* What every Python caller of the reference runs right after the build (utils_3d.py:77-90): SignedDistanceField::
  * GetFullGradient (sdf.hpp:341-358) over GetGridAlignedGradient (sdf.hpp:432-526) -- central differences, one-sided

@@ -157,40 +157,24 @@ inline std::pair<sdf_tools::SignedDistanceField, std::pair<double, double>> Extr
     if (!add_virtual_border)
         return ExtractSignedDistanceField<T>(grid.GetOriginTransform(), cell_sizes.x(), nx, ny, nz, is_filled_fn, oob_value, frame);
 
-    // Virtual border: axes longer than one cell grow by a one-cell shell.  The shell is FILLED in the field that
-    // supplies the free-space (>= 0) values and FREE in the field that supplies the inside (<= 0) values.
-    const int64_t ox = nx > 1 ? 1 : 0, oy = ny > 1 ? 1 : 0, oz = nz > 1 ? 1 : 0;
-    const int64_t bx = nx + 2 * ox, by = ny + 2 * oy, bz = nz + 2 * oz;
-    std::vector<uint8_t> inner((size_t)(nx * ny * nz));
-    {
-        size_t i = 0;                                   // one predicate call per real voxel, x -> y -> z
+    // Virtual border (reference :287-419): axes longer than one cell grow by a one-cell shell, FILLED in the build that
+    // supplies the free-space (>= 0) values and FREE in the build that supplies the inside (<= 0) values; the two
+    // padded builds, the per-voxel select and the extrema run on the device (sdf_b200_build_with_border).  The predicate is
+    // called once per real voxel in EACH of two x -> y -> z sweeps, as the reference's two extractions do (:381-382).
+    const size_t N = (size_t)(nx * ny * nz);
+    std::vector<uint8_t> inner_free(N), inner_filled(N);
+    for (std::vector<uint8_t>* m : {&inner_free, &inner_filled}) {
+        size_t i = 0;
         for (int64_t x = 0; x < nx; ++x)
             for (int64_t y = 0; y < ny; ++y)
-                for (int64_t z = 0; z < nz; ++z) inner[i++] = is_filled_fn(VoxelGrid::GRID_INDEX(x, y, z)) ? 1 : 0;
+                for (int64_t z = 0; z < nz; ++z) (*m)[i++] = is_filled_fn(VoxelGrid::GRID_INDEX(x, y, z)) ? 1 : 0;
     }
-    auto padded = [&](uint8_t shell) {
-        std::vector<uint8_t> m((size_t)(bx * by * bz), shell);
-        for (int64_t x = 0; x < nx; ++x)
-            for (int64_t y = 0; y < ny; ++y)
-                for (int64_t z = 0; z < nz; ++z)
-                    m[(size_t)(((x + ox) * by + (y + oy)) * bz + (z + oz))] = inner[(size_t)((x * ny + y) * nz + z)];
-        return m;
-    };
-    const auto free_res = detail::BuildFromMask(grid.GetOriginTransform(), cell_sizes.x(), bx, by, bz, padded(1), oob_value, frame);
-    const auto filled_res = detail::BuildFromMask(grid.GetOriginTransform(), cell_sizes.x(), bx, by, bz, padded(0), oob_value, frame);
     sdf_tools::SignedDistanceField combined(grid.GetOriginTransform(), frame, cell_sizes.x(), nx, ny, nz, oob_value);
-    std::vector<float> values((size_t)(nx * ny * nz));
-    const std::vector<float>& fr = free_res.first.GetImmutableRawData();
-    const std::vector<float>& fi = filled_res.first.GetImmutableRawData();
-    for (int64_t x = 0; x < nx; ++x)
-        for (int64_t y = 0; y < ny; ++y)
-            for (int64_t z = 0; z < nz; ++z) {
-                const size_t q = (size_t)(((x + ox) * by + (y + oy)) * bz + (z + oz));
-                const float a = fr[q], b = fi[q];
-                values[(size_t)((x * ny + y) * nz + z)] = (a >= 0.0f) ? a : ((b <= -0.0f) ? b : 0.0f);
-            }
-    combined.AdoptData(std::move(values));
-    return std::make_pair(combined, std::make_pair(free_res.second.first, filled_res.second.second));
+    double mx = 0.0, mn = 0.0;
+    sdf_b200_ctx* ctx = detail::Context();
+    detail::Check(sdf_b200_build_with_border(ctx, inner_free.data(), inner_filled.data(), nx, ny, nz, cell_sizes.x(),
+                                             combined.GetMutableRawData().data(), &mx, &mn), ctx);
+    return std::make_pair(std::move(combined), std::make_pair(mx, mn));
 }
 
 // Grid + value predicate (reference :422-441).

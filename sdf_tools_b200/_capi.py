@@ -39,6 +39,8 @@ SYMBOLS = [
     ("sdf_b200_slab_summary_scatter_device", _int, [_vp, _vp, _i64, _i64, _i64, C.POINTER(_vp), _int, _int]),
     ("sdf_b200_get_extrema_raw", _int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("sdf_b200_extrema_from_raw", _int, [C.c_int32, C.c_int32, _dbl, _pd, _pd]),
+    ("sdf_b200_build_with_border", _int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _vp, _pd, _pd]),
+    ("sdf_b200_build_object_sdfs", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _vp, _int, _vp, _pd, _pd]),
     ("sdf_b200_gradient_device", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _vp]),
     ("sdf_b200_gradient_host", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _vp]),
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),

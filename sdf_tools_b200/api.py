@@ -20,6 +20,9 @@ class SdfB200Error(RuntimeError):
 
 
 COLLISION_CELL_DTYPE = np.dtype([("occupancy", np.float32), ("component", np.uint32)])
+TAGGED_CELL_DTYPE = np.dtype([("occupancy", np.float32), ("component", np.uint32), ("object_id", np.uint32),
+                              ("convex_segment", np.uint32)])            # tagged_object_collision_map.hpp:22-43
+QUERY_OBJECT, QUERY_ANY, QUERY_NAMED = 0, 1, 2
 
 
 def _check_out(out, shape):
@@ -105,6 +108,53 @@ class Context:
                                                         *c.shape, float(resolution), out.ctypes.data,
                                                         C.byref(mx), C.byref(mn)))
         return out, (mx.value, mn.value)
+
+    def build_with_border(self, mask: np.ndarray, resolution: float, mask_second: np.ndarray | None = None):
+        """add_virtual_border = true (sdf_b200_build_with_border): (sdf (nx,ny,nz) f32, (max, min)).  mask_second: the
+        predicate as the reference's SECOND extraction would see it (stateful predicates); default: the same mask."""
+        m = np.ascontiguousarray(mask)
+        if m.dtype != np.uint8:
+            m = (m != 0).astype(np.uint8)
+        if m.ndim != 3:
+            raise ValueError("mask must have shape (nx, ny, nz)")
+        m2 = m if mask_second is None else np.ascontiguousarray((np.asarray(mask_second) != 0).astype(np.uint8))
+        if m2.shape != m.shape:
+            raise ValueError("mask_second must have the shape of mask")
+        out = np.empty(m.shape, dtype=np.float32)
+        mx, mn = C.c_double(), C.c_double()
+        self._check(self._lib.sdf_b200_build_with_border(self._h, m.ctypes.data, m2.ctypes.data, *m.shape, float(resolution),
+                                                         out.ctypes.data, C.byref(mx), C.byref(mn)))
+        return out, (mx.value, mn.value)
+
+    def build_object_sdfs(self, tagged_cells: np.ndarray, resolution: float, queries, unknown_is_filled: bool = False):
+        """Batched TaggedObjectCollisionMapGrid SDFs (sdf_b200_build_object_sdfs).  tagged_cells: (nx,ny,nz) of
+        TAGGED_CELL_DTYPE; queries: object ids (ints: cells of that object) or (object_id, kind) pairs with kind in
+        QUERY_OBJECT / QUERY_ANY / QUERY_NAMED.  Returns (sdfs (nq,nx,ny,nz) float32, [(max, min)] * nq)."""
+        c = np.ascontiguousarray(tagged_cells)
+        if c.ndim != 3 or c.dtype != TAGGED_CELL_DTYPE:
+            raise ValueError("tagged_cells must be (nx,ny,nz) of TAGGED_CELL_DTYPE (16-byte records)")
+        qs = [(int(q), QUERY_OBJECT) if np.isscalar(q) else (int(q[0]), int(q[1])) for q in queries]
+        arr = np.array(qs, dtype=np.uint32).reshape(-1, 2)
+        out = np.empty((len(qs),) + c.shape, dtype=np.float32)
+        mx = (C.c_double * max(len(qs), 1))()
+        mn = (C.c_double * max(len(qs), 1))()
+        self._check(self._lib.sdf_b200_build_object_sdfs(self._h, c.ctypes.data, *c.shape, float(resolution),
+                                                         int(bool(unknown_is_filled)), arr.ctypes.data, len(qs),
+                                                         out.ctypes.data, mx, mn))
+        return out, [(mx[k], mn[k]) for k in range(len(qs))]
+
+    def gradient(self, sdf: np.ndarray, resolution: float, enable_edge_gradients: bool = True, dtype=np.float64):
+        """(nx,ny,nz,3) grid-aligned gradient field of an f32 SDF (sdf_b200_gradient_host; reference sdf.hpp:341-358, :432-526)."""
+        f = np.ascontiguousarray(sdf, dtype=np.float32)
+        if f.ndim != 3:
+            raise ValueError("sdf must have shape (nx, ny, nz)")
+        if np.dtype(dtype) not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("dtype must be float64 or float32")
+        out = np.empty(f.shape + (3,), dtype=dtype)
+        self._check(self._lib.sdf_b200_gradient_host(self._h, f.ctypes.data, *f.shape, float(resolution),
+                                                     int(bool(enable_edge_gradients)), int(np.dtype(dtype) == np.float64),
+                                                     out.ctypes.data))
+        return out
 
     # -------------------------------------------------------------------------------------- device buffers
     def set_stream(self, cuda_stream_ptr: int | None):

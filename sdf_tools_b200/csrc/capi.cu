@@ -26,12 +26,15 @@ struct sdf_b200_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;  // host entry points: H2D / D2H chunks overlap the kernels of the other chunks
     cudaEvent_t chunk_ev[17] = {};       // [0..7] upload chunks, [8..15] download chunks, [16] stream hand-over
+    cudaEvent_t pack_ev[2] = {};         // cells staging halves: the pack kernel that read them has finished
     bool timed = false;
     int launches = 0;
     void* d_in = nullptr;  size_t in_bytes = 0;     // staging for the host entry points
     void* d_mask = nullptr; size_t mask_bytes = 0;
     void* d_out = nullptr; size_t out_bytes = 0;
     void* d_grad = nullptr; size_t grad_bytes = 0;  // gradient staging of the host entry point
+    void* d_out2 = nullptr; size_t out2_bytes = 0;  // second result buffer of the batched object builds
+    int* d_ext_objs = nullptr; size_t ext_objs_n = 0;
     int64_t last_dims[3] = {0, 0, 0};               // grid of the last HOST build whose field is still in d_out
     double res = 1.0;
     bool built = false;
@@ -112,6 +115,7 @@ int sdf_b200_create(sdf_b200_ctx** out, int device)
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 17 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->pack_ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create: events / copy stream", e);
         sdf_b200_destroy(ctx);
@@ -140,6 +144,7 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 17; ++i) if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    for (int i = 0; i < 2; ++i) if (ctx->pack_ev[i]) cudaEventDestroy(ctx->pack_ev[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->d_ext) cudaFree(ctx->d_ext);
     if (ctx->d_dbg) cudaFree(ctx->d_dbg);
@@ -150,6 +155,8 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_grad) cudaFree(ctx->d_grad);
+    if (ctx->d_out2) cudaFree(ctx->d_out2);
+    if (ctx->d_ext_objs) cudaFree(ctx->d_ext_objs);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -189,7 +196,8 @@ int sdf_b200_host_free(void* p)
 
 // mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in place in d_field
 static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz, double res,
-                      int32_t* d_field, bool final_pass, const void* d_carries = nullptr, bool keep_extrema = false)
+                      int32_t* d_field, bool final_pass, const void* d_carries = nullptr, bool keep_extrema = false,
+                      unsigned mask_bits = 0xffu)
 {
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
@@ -204,7 +212,7 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[0], st), "event");
-    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, d_carries, st), "launch binary_z");
+    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
@@ -580,15 +588,19 @@ static int build_host_common(sdf_b200_ctx* ctx, const void* h_in, size_t in_byte
 //   column-chunks of the final x pass (a y range, all z): each finishes every x of its columns, so its result leaves
 //               with one strided D2H (nx rows of ychunk*nz floats) while the next chunk is still computing.
 // Result and extrema are identical to the unpipelined path: chunks only partition independent lines.
-static int build_host_pipelined(sdf_b200_ctx* ctx, const uint8_t* h_mask, int64_t nx, int64_t ny, int64_t nz, double res,
-                                float* out_sdf, double* out_max, double* out_min)
+static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cells, int unknown_is_filled, int64_t nx,
+                                int64_t ny, int64_t nz, double res, float* out_sdf, double* out_max, double* out_min)
 {
     constexpr int NCH = 8;
     constexpr int LUT_N = 1 << 20;
     const int64_t N = nx * ny * nz, plane = ny * nz;
+    const uint8_t* h_mask = (const uint8_t*)h_in;
     int rc;
     if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)N))) return rc;
     if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+    // cells (8 B per voxel): two x-chunks of staging, used alternately, so the upload of chunk i+1 overlaps the pack of chunk i
+    const int64_t chunk_planes = (nx + NCH - 1) / NCH;
+    if (is_cells && (rc = grow(ctx, &ctx->d_in, &ctx->in_bytes, (size_t)(2 * chunk_planes * plane) * 8))) return rc;
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     uint8_t* d_mask = (uint8_t*)ctx->d_mask;
     int32_t* d_field = (int32_t*)ctx->d_out;
@@ -607,9 +619,20 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const uint8_t* h_mask, int64_
         const int64_t x0 = nx * i / NCH, x1 = nx * (i + 1) / NCH;
         if (x1 == x0) continue;
         const int64_t off = x0 * plane, cnt = (x1 - x0) * plane;
-        CK(cudaMemcpyAsync(d_mask + off, h_mask + off, (size_t)cnt, cudaMemcpyHostToDevice, cs), "H2D mask chunk");
-        CK(cudaEventRecord(ctx->chunk_ev[i], cs), "event");
-        CK(cudaStreamWaitEvent(st, ctx->chunk_ev[i], 0), "wait");
+        if (is_cells) {
+            char* stage = (char*)ctx->d_in + (size_t)(i & 1) * (size_t)(chunk_planes * plane) * 8;
+            if (i >= 2) CK(cudaStreamWaitEvent(cs, ctx->pack_ev[i & 1], 0), "wait for the staging half");   // its previous pack is done
+            CK(cudaMemcpyAsync(stage, (const char*)h_in + (size_t)off * 8, (size_t)cnt * 8, cudaMemcpyHostToDevice, cs), "H2D cells chunk");
+            CK(cudaEventRecord(ctx->chunk_ev[i], cs), "event");
+            CK(cudaStreamWaitEvent(st, ctx->chunk_ev[i], 0), "wait");
+            CK(sdfb200::launch_pack_cells(stage, cnt, unknown_is_filled, d_mask + off, st), "launch pack_cells");
+            CK(cudaEventRecord(ctx->pack_ev[i & 1], st), "event");
+            ctx->launches++;
+        } else {
+            CK(cudaMemcpyAsync(d_mask + off, h_mask + off, (size_t)cnt, cudaMemcpyHostToDevice, cs), "H2D mask chunk");
+            CK(cudaEventRecord(ctx->chunk_ev[i], cs), "event");
+            CK(cudaStreamWaitEvent(st, ctx->chunk_ev[i], 0), "wait");
+        }
         CK(sdfb200::launch_binary_z(d_mask + off, d_field + off, (int)nz, (x1 - x0) * ny, nullptr, st), "launch binary_z");
         ctx->launches++;
         if (ny > 1) {
@@ -645,7 +668,7 @@ int sdf_b200_build_from_mask(sdf_b200_ctx* ctx, const uint8_t* mask, int64_t nx,
     if (ctx && mask && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx >= 64 && ny >= 64 &&
         nx * ny * nz >= ((int64_t)1 << 25)) {           // big enough for the copies to be worth overlapping
         CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-        return build_host_pipelined(ctx, mask, nx, ny, nz, resolution, out_sdf, out_max, out_min);
+        return build_host_pipelined(ctx, mask, false, 0, nx, ny, nz, resolution, out_sdf, out_max, out_min);
     }
     return build_host_common(ctx, mask, (size_t)(nx * ny * nz), false, 0, nx, ny, nz, resolution, out_sdf, out_max, out_min);
 }
@@ -655,6 +678,11 @@ int sdf_b200_build_from_cells(sdf_b200_ctx* ctx, const void* cells, int unknown_
 {
     if (ctx && ctx->peers.size() > 1 && cells && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx * ny * nz > 0)
         return build_multi_host(ctx, cells, true, unknown_is_filled, nx, ny, nz, resolution, out_sdf, out_max, out_min);
+    if (ctx && cells && out_sdf && check_dims(ctx, nx, ny, nz) == SDF_B200_OK && nx >= 64 && ny >= 64 &&
+        nx * ny * nz >= ((int64_t)1 << 25)) {           // big enough for the copies to be worth overlapping
+        CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+        return build_host_pipelined(ctx, cells, true, unknown_is_filled, nx, ny, nz, resolution, out_sdf, out_max, out_min);
+    }
     return build_host_common(ctx, cells, (size_t)(nx * ny * nz) * 8, true, unknown_is_filled, nx, ny, nz, resolution,
                              out_sdf, out_max, out_min);
 }
@@ -812,6 +840,124 @@ int sdf_b200_gradient_host(sdf_b200_ctx* ctx, const float* sdf, int64_t nx, int6
        "launch gradient");
     CK(cudaMemcpyAsync(out_grad, ctx->d_grad, (size_t)N * 3 * esz, cudaMemcpyDeviceToHost, st), "D2H gradient");
     CK(cudaStreamSynchronize(st), "sync");
+    return SDF_B200_OK;
+}
+
+// Batched object SDFs: the 16-byte tagged cells go to the device ONCE; every pass over them answers up to 8 queries
+// (one mask bit each); the builds then run back to back on the compute stream while the copy stream downloads the
+// previous result from the other of two result buffers.
+int sdf_b200_build_object_sdfs(sdf_b200_ctx* ctx, const void* tagged_cells, int64_t nx, int64_t ny, int64_t nz,
+                               double resolution, int unknown_is_filled, const sdf_b200_object_query* queries, int nqueries,
+                               float* out_sdfs, double* out_max, double* out_min)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    int rc = check_dims(ctx, nx, ny, nz);
+    if (rc) return rc;
+    if (nqueries < 0 || (nqueries > 0 && !queries)) return fail(ctx, SDF_B200_ERR_ARG, "bad query list");
+    for (int k = 0; k < nqueries; ++k) if (queries[k].kind > 2u) return fail(ctx, SDF_B200_ERR_ARG, "unknown query kind");
+    const int64_t N = nx * ny * nz;
+    if (nqueries == 0) return SDF_B200_OK;
+    if (N > 0 && (!tagged_cells || !out_sdfs)) return fail(ctx, SDF_B200_ERR_ARG, "null host pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const double inf = std::numeric_limits<double>::infinity();
+    if (N == 0) {
+        for (int k = 0; k < nqueries; ++k) { if (out_max) out_max[k] = -inf; if (out_min) out_min[k] = inf; }
+        return SDF_B200_OK;
+    }
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->in_bytes, (size_t)N * 16))) return rc;
+    if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)N))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)N * 4))) return rc;
+    if ((rc = grow(ctx, &ctx->d_out2, &ctx->out2_bytes, (size_t)N * 4))) return rc;
+    if (ctx->ext_objs_n < (size_t)nqueries) {
+        if (ctx->d_ext_objs) cudaFree(ctx->d_ext_objs);
+        ctx->d_ext_objs = nullptr; ctx->ext_objs_n = 0;
+        CK(cudaMalloc(&ctx->d_ext_objs, (size_t)nqueries * 2 * sizeof(int)), "cudaMalloc(object extrema)");
+        ctx->ext_objs_n = (size_t)nqueries;
+    }
+    CK(cudaMemcpyAsync(ctx->d_in, tagged_cells, (size_t)N * 16, cudaMemcpyHostToDevice, st), "H2D tagged cells");
+    int launches = 0;
+    for (int k0 = 0; k0 < nqueries; k0 += 8) {
+        const int nq = nqueries - k0 < 8 ? nqueries - k0 : 8;
+        uint32_t ids[8], kinds[8];
+        for (int q = 0; q < nq; ++q) { ids[q] = queries[k0 + q].object_id; kinds[q] = queries[k0 + q].kind; }
+        CK(sdfb200::launch_pack_tagged(ctx->d_in, N, unknown_is_filled, ids, kinds, nq, (uint8_t*)ctx->d_mask, st), "launch pack_tagged");
+        ++launches;
+        for (int q = 0; q < nq; ++q) {
+            const int k = k0 + q;
+            void* buf = (k & 1) ? ctx->d_out2 : ctx->d_out;
+            if (k >= 2) CK(cudaStreamWaitEvent(st, ctx->chunk_ev[8 + (k & 1)], 0), "wait for the download of this buffer");
+            rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, nx, ny, nz, resolution, (int32_t*)buf, true, nullptr, false, 1u << q);
+            if (rc) return rc;
+            launches += ctx->launches;
+            CK(cudaMemcpyAsync(ctx->d_ext_objs + 2 * k, ctx->d_ext, 2 * sizeof(int), cudaMemcpyDeviceToDevice, st), "keep extrema");
+            CK(cudaEventRecord(ctx->chunk_ev[k & 1], st), "event");
+            CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[k & 1], 0), "wait");
+            CK(cudaMemcpyAsync(out_sdfs + (size_t)k * N, buf, (size_t)N * 4, cudaMemcpyDeviceToHost, cs), "D2H object sdf");
+            CK(cudaEventRecord(ctx->chunk_ev[8 + (k & 1)], cs), "event");
+        }
+    }
+    std::vector<int> raw((size_t)nqueries * 2);
+    CK(cudaMemcpyAsync(raw.data(), ctx->d_ext_objs, raw.size() * sizeof(int), cudaMemcpyDeviceToHost, st), "copy extrema");
+    CK(cudaStreamSynchronize(st), "sync");
+    CK(cudaStreamSynchronize(cs), "sync copies");
+    for (int k = 0; k < nqueries; ++k)
+        sdf_b200_extrema_from_raw(raw[2 * k], raw[2 * k + 1], resolution, out_max ? out_max + k : nullptr, out_min ? out_min + k : nullptr);
+    ctx->launches = launches;
+    ctx->last_dims[0] = ctx->last_dims[1] = ctx->last_dims[2] = 0;      // d_out no longer holds "the" field of a host build
+    return SDF_B200_OK;
+}
+
+// add_virtual_border on the device: one upload of the inner mask(s), two builds on the padded grid, fused select, one
+// download of the real grid.  mask_free / mask_filled: the caller's predicate evaluated for the free-space build and for
+// the inside build (the reference calls it once per voxel in EACH of its two extractions, sdf_generation.hpp:381-382);
+// pass the same pointer twice for a pure predicate.
+int sdf_b200_build_with_border(sdf_b200_ctx* ctx, const uint8_t* mask_free, const uint8_t* mask_filled, int64_t nx, int64_t ny,
+                               int64_t nz, double resolution, float* out_sdf, double* out_max, double* out_min)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    const int ox = nx > 1 ? 1 : 0, oy = ny > 1 ? 1 : 0, oz = nz > 1 ? 1 : 0;
+    const int64_t bx = nx + 2 * ox, by = ny + 2 * oy, bz = nz + 2 * oz;
+    int rc = check_dims(ctx, bx, by, bz);
+    if (rc) return rc;
+    const int64_t N = nx * ny * nz, NB = bx * by * bz;
+    const double inf = std::numeric_limits<double>::infinity();
+    if (N == 0) { if (out_max) *out_max = -inf; if (out_min) *out_min = inf; return SDF_B200_OK; }
+    if (!mask_free || !mask_filled || !out_sdf) return fail(ctx, SDF_B200_ERR_ARG, "null host pointer");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    cudaStream_t st = ctx->stream;
+    const bool same = mask_free == mask_filled;
+    if ((rc = grow(ctx, &ctx->d_in, &ctx->in_bytes, (size_t)N * (same ? 1 : 2)))) return rc;       // inner mask(s)
+    if ((rc = grow(ctx, &ctx->d_mask, &ctx->mask_bytes, (size_t)NB))) return rc;                   // padded mask
+    if ((rc = grow(ctx, &ctx->d_out, &ctx->out_bytes, (size_t)NB * 4))) return rc;                 // padded free-space field
+    if ((rc = grow(ctx, &ctx->d_out2, &ctx->out2_bytes, (size_t)NB * 4))) return rc;               // padded inside field
+    if ((rc = grow(ctx, &ctx->d_grad, &ctx->grad_bytes, (size_t)N * 4))) return rc;                // combined field (staging)
+    uint8_t* d_inner = (uint8_t*)ctx->d_in;
+    CK(cudaMemcpyAsync(d_inner, mask_free, (size_t)N, cudaMemcpyHostToDevice, st), "H2D mask");
+    if (!same) CK(cudaMemcpyAsync(d_inner + N, mask_filled, (size_t)N, cudaMemcpyHostToDevice, st), "H2D mask");
+    int launches = 0, raw_free[2] = {0, 0}, raw_filled[2] = {0, 0};
+    // free-space build: shell FILLED; its max is the combined max (:412-413)
+    CK(sdfb200::launch_border_pad(d_inner, nx, ny, nz, ox, oy, oz, 1, (uint8_t*)ctx->d_mask, st), "launch border_pad");
+    if ((rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, bx, by, bz, resolution, (int32_t*)ctx->d_out, true))) return rc;
+    launches += ctx->launches + 1;
+    CK(cudaMemcpyAsync(raw_free, ctx->d_ext, sizeof(raw_free), cudaMemcpyDeviceToHost, st), "copy extrema");
+    // inside build: shell FREE; its min is the combined min
+    CK(sdfb200::launch_border_pad(same ? d_inner : d_inner + N, nx, ny, nz, ox, oy, oz, 0, (uint8_t*)ctx->d_mask, st), "launch border_pad");
+    if ((rc = run_passes(ctx, (const uint8_t*)ctx->d_mask, bx, by, bz, resolution, (int32_t*)ctx->d_out2, true))) return rc;
+    launches += ctx->launches + 1;
+    CK(cudaMemcpyAsync(raw_filled, ctx->d_ext, sizeof(raw_filled), cudaMemcpyDeviceToHost, st), "copy extrema");
+    CK(sdfb200::launch_border_select((const float*)ctx->d_out, (const float*)ctx->d_out2, nx, ny, nz, ox, oy, oz, (float*)ctx->d_grad, st),
+       "launch border_select");
+    ++launches;
+    CK(cudaMemcpyAsync(out_sdf, ctx->d_grad, (size_t)N * 4, cudaMemcpyDeviceToHost, st), "D2H sdf");
+    CK(cudaStreamSynchronize(st), "sync");
+    ctx->launches = launches;
+    ctx->last_dims[0] = ctx->last_dims[1] = ctx->last_dims[2] = 0;
+    double mx = 0, mn = 0, dummy = 0;
+    sdf_b200_extrema_from_raw(raw_free[0], raw_free[1], resolution, &mx, &dummy);
+    sdf_b200_extrema_from_raw(raw_filled[0], raw_filled[1], resolution, &dummy, &mn);
+    if (out_max) *out_max = mx;
+    if (out_min) *out_min = mn;
     return SDF_B200_OK;
 }
 

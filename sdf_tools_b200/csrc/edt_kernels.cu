@@ -48,6 +48,31 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const float2* __restric
     }
 }
 
+// TAGGED_OBJECT_COLLISION_CELL {float occupancy; u32 component; u32 object_id; u32 convex_segment} (16 B, reference
+// tagged_object_collision_map.hpp:22-43) -> one byte per voxel whose bit q answers query q (up to 8 per pass):
+//   kind 0: filled and object_id == id   (ExtractSignedDistanceField(objects_to_use = {id}), :813-856; MakeObjectSDFs :875-915)
+//   kind 1: filled                        (objects_to_use empty; the "free" field of :733-753)
+//   kind 2: filled and object_id > 0      (the "named objects" field of :755-778)
+// with filled = occupancy > 0.5 || (unknown_is_filled && occupancy == 0.5).  The binary pass then reads bit q through
+// its selector, so one read of the 16-byte cells serves 8 object SDFs.
+struct TaggedQueries { uint32_t id[8]; uint32_t kind[8]; int n; };
+__global__ void __launch_bounds__(256) pack_tagged_kernel(const uint4* __restrict__ cells, int64_t n, int unknown_is_filled,
+                                                          TaggedQueries q, uint8_t* __restrict__ mask)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 c = __ldg(cells + i);
+    const float occ = __uint_as_float(c.x);
+    const bool filled = (occ > 0.5f) || (unknown_is_filled && occ == 0.5f);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool hit = q.kind[k] == 0 ? (c.z == q.id[k]) : (q.kind[k] == 1 ? true : c.z > 0u);
+        bits |= (uint32_t)(k < q.n && filled && hit) << k;
+    }
+    mask[i] = (uint8_t)bits;
+}
+
 // ============================================================================================ K1 binary z
 // Binary pass along the contiguous z axis: s(z) = +-min(z-a+1, e-z)^2 with [a,e) the run of equal polarity around z
 // (squared distance to the nearest voxel of the other polarity on the line; SDF_INF if there is none).
@@ -57,13 +82,13 @@ __global__ void __launch_bounds__(256) pack_cells_kernel(const float2* __restric
 // counters, and the warp's 32x32 block is transposed through a padded shared tile so rows leave as 128-byte stores.
 // carries (slab builds): per line {distance from z=0 / z=nz-1 to the nearest other-polarity voxel in the slabs below /
 // above}, FARB = none.
-__device__ __forceinline__ uint32_t pack_nonzero_bytes16(uint4 x)
+__device__ __forceinline__ uint32_t pack_nonzero_bytes16(uint4 x, uint32_t sel)
 {
     const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
     uint32_t bits = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint32_t t = __vcmpne4(xs[q], 0u) & 0x01010101u;          // 1 per non-zero byte
+        const uint32_t t = __vcmpne4(xs[q] & sel, 0u) & 0x01010101u;    // 1 per byte with a selected bit set
         bits |= (((t * 0x01020408u) >> 24) & 0xFu) << (4 * q);
     }
     return bits;
@@ -71,8 +96,9 @@ __device__ __forceinline__ uint32_t pack_nonzero_bytes16(uint4 x)
 
 template <int LPL, int WPL>   // lanes per line; words per lane (WPL = 2 only with LPL = 32, for nz in (1024, 2048])
 __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ out,
-                                                       int nz, int64_t nlines, const int2* __restrict__ carries)
-{
+                                                       int nz, int64_t nlines, const int2* __restrict__ carries, uint32_t sel)
+{   // sel: which bits of a mask byte mean FILLED, replicated in all four bytes (0xffffffff: any; 0x01010101 << k: bit k
+    // of a multi-object mask, see pack_tagged_kernel)
     static_assert(WPL == 1 || LPL == 32, "two words per lane only for full-warp lines");
     __shared__ int32_t tile_all[8][32 * 33];
     constexpr int LNW = 32 / LPL;               // lines per warp
@@ -96,10 +122,10 @@ __global__ void __launch_bounds__(256) binary_z_kernel(const uint8_t* __restrict
         uint32_t p = 0;
         if (line_ok && z0 < nz) {
             if (vec16) {
-                p = pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0)));
-                if (z0 + 16 < nz) p |= pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0 + 16))) << 16;
+                p = pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0)), sel);
+                if (z0 + 16 < nz) p |= pack_nonzero_bytes16(__ldg(reinterpret_cast<const uint4*>(mp + z0 + 16)), sel) << 16;
             } else {
-                for (int j = 0; j < 32 && z0 + j < nz; ++j) p |= (uint32_t)(__ldg(mp + z0 + j) != 0) << j;
+                for (int j = 0; j < 32 && z0 + j < nz; ++j) p |= (uint32_t)((__ldg(mp + z0 + j) & sel) != 0) << j;
             }
         }
         P[k] = p;
@@ -430,6 +456,52 @@ __global__ void __launch_bounds__(NBMAX * LPC, (NBMAX * LPC == 512) ? 3 : 1) ban
     }
 }
 
+// ============================================================================================== virtual border
+// add_virtual_border (reference sdf_generation.hpp:287-419): axes longer than one cell grow by a one-cell shell that is
+// FILLED in the build that supplies the free-space values and FREE in the build that supplies the inside values.
+// pad: inner mask (nx,ny,nz) -> padded mask (nx+2ox, ny+2oy, nz+2oz) with the shell set to `shell`;
+// select: per real voxel  a >= 0 ? a : (b <= -0 ? b : 0)  from the two padded fields (:381-409).
+__global__ void __launch_bounds__(256) border_pad_kernel(const uint8_t* __restrict__ inner, int64_t nx, int64_t ny, int64_t nz,
+                                                         int ox, int oy, int oz, uint8_t shell, uint8_t* __restrict__ padded)
+{
+    const int64_t bx = nx + 2 * ox, by = ny + 2 * oy, bz = nz + 2 * oz;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bx * by * bz) return;
+    const int64_t z = i % bz - oz, y = (i / bz) % by - oy, x = i / (bz * by) - ox;
+    const bool in = x >= 0 && x < nx && y >= 0 && y < ny && z >= 0 && z < nz;
+    padded[i] = in ? (uint8_t)(__ldg(inner + (x * ny + y) * nz + z) != 0) : shell;
+}
+
+__global__ void __launch_bounds__(256) border_select_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t nx,
+                                                            int64_t ny, int64_t nz, int ox, int oy, int oz, float* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx * ny * nz) return;
+    const int64_t z = i % nz, y = (i / nz) % ny, x = i / (nz * ny);
+    const int64_t by = ny + 2 * oy, bz = nz + 2 * oz;
+    const int64_t q = ((x + ox) * by + (y + oy)) * bz + (z + oz);
+    const float fa = __ldg(a + q), fb = __ldg(b + q);
+    out[i] = (fa >= 0.0f) ? fa : ((fb <= -0.0f) ? fb : 0.0f);
+}
+
+cudaError_t launch_border_pad(const uint8_t* d_inner, int64_t nx, int64_t ny, int64_t nz, int ox, int oy, int oz, int shell,
+                              uint8_t* d_padded, cudaStream_t st)
+{
+    const int64_t n = (nx + 2 * ox) * (ny + 2 * oy) * (nz + 2 * oz);
+    if (n <= 0) return cudaSuccess;
+    border_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_inner, nx, ny, nz, ox, oy, oz, (uint8_t)(shell != 0), d_padded);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_border_select(const float* d_a, const float* d_b, int64_t nx, int64_t ny, int64_t nz, int ox, int oy, int oz,
+                                 float* d_out, cudaStream_t st)
+{
+    const int64_t n = nx * ny * nz;
+    if (n <= 0) return cudaSuccess;
+    border_select_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, d_b, nx, ny, nz, ox, oy, oz, d_out);
+    return cudaGetLastError();
+}
+
 // ============================================================================================== gradient field
 // Grid-aligned gradient of a finished SDF, one thread per voxel: SignedDistanceField::GetGridAlignedGradient
 // (/root/reference/include/sdf_tools/sdf.hpp:432-526) evaluated for every voxel as GetFullGradient does (:341-358).
@@ -494,6 +566,19 @@ cudaError_t launch_pack_cells(const void* d_cells, int64_t n, int unknown_is_fil
     return cudaGetLastError();
 }
 
+cudaError_t launch_pack_tagged(const void* d_cells16, int64_t n, int unknown_is_filled, const uint32_t* ids,
+                               const uint32_t* kinds, int nq, uint8_t* d_mask, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    if (nq < 1 || nq > 8) return cudaErrorInvalidValue;
+    TaggedQueries q;
+    for (int k = 0; k < 8; ++k) { q.id[k] = k < nq ? ids[k] : 0u; q.kind[k] = k < nq ? kinds[k] : 0u; }
+    q.n = nq;
+    pack_tagged_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(d_cells16), n,
+                                                                    unknown_is_filled, q, d_mask);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
@@ -502,25 +587,26 @@ cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st)
 }
 
 template <int LPL, int WPL>
-static cudaError_t launch_binary_z_cfg(const uint8_t* m, int32_t* out, int nz, int64_t nlines, const int2* cy, cudaStream_t st)
+static cudaError_t launch_binary_z_cfg(const uint8_t* m, int32_t* out, int nz, int64_t nlines, const int2* cy, uint32_t sel, cudaStream_t st)
 {
     const int wpb = 8;
     const int64_t lines_per_block = (int64_t)wpb * (32 / LPL);
-    binary_z_kernel<LPL, WPL><<<(unsigned)((nlines + lines_per_block - 1) / lines_per_block), wpb * 32, 0, st>>>(m, out, nz, nlines, cy);
+    binary_z_kernel<LPL, WPL><<<(unsigned)((nlines + lines_per_block - 1) / lines_per_block), wpb * 32, 0, st>>>(m, out, nz, nlines, cy, sel);
     return cudaGetLastError();
 }
 
 cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, const void* d_carries,
-                            cudaStream_t st)
+                            cudaStream_t st, unsigned mask_bits)
 {
     const int2* cy = reinterpret_cast<const int2*>(d_carries);
-    if (nz <= 32) return launch_binary_z_cfg<1, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 64) return launch_binary_z_cfg<2, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 128) return launch_binary_z_cfg<4, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 256) return launch_binary_z_cfg<8, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 512) return launch_binary_z_cfg<16, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 1024) return launch_binary_z_cfg<32, 1>(d_mask, d_out, nz, nlines, cy, st);
-    if (nz <= 2048) return launch_binary_z_cfg<32, 2>(d_mask, d_out, nz, nlines, cy, st);
+    const uint32_t sel = (mask_bits & 0xffu) * 0x01010101u;
+    if (nz <= 32) return launch_binary_z_cfg<1, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 64) return launch_binary_z_cfg<2, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 128) return launch_binary_z_cfg<4, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 256) return launch_binary_z_cfg<8, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 512) return launch_binary_z_cfg<16, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 1024) return launch_binary_z_cfg<32, 1>(d_mask, d_out, nz, nlines, cy, sel, st);
+    if (nz <= 2048) return launch_binary_z_cfg<32, 2>(d_mask, d_out, nz, nlines, cy, sel, st);
     return cudaErrorInvalidValue;
 }
 

@@ -13,8 +13,14 @@ cudaError_t launch_pack_cells(const void* d_cells, int64_t n, int unknown_is_fil
 // K1: binary pass along the contiguous z axis.  mask[nlines][nz] -> signed int32 d^2 along z
 //     d_carries: NULL, or per line {distance from z=0 / z=nz-1 to the nearest other-polarity voxel in the slabs
 //     below / above} (int2, 40000 = none) for slab builds.
+//     mask_bits: which bits of a mask byte mean FILLED (0xff: any non-zero byte; 1 << q: query q of launch_pack_tagged)
 cudaError_t launch_binary_z(const uint8_t* d_mask, int32_t* d_out, int nz, int64_t nlines, const void* d_carries,
-                            cudaStream_t st);
+                            cudaStream_t st, unsigned mask_bits = 0xffu);
+
+// TAGGED_OBJECT_COLLISION_CELL[n] (16 B each) -> one byte per voxel, bit q = "filled and matches query q" (nq <= 8;
+// kinds: 0 object_id == ids[q], 1 any cell, 2 object_id > 0): tagged_object_collision_map.hpp:733-778, :813-856
+cudaError_t launch_pack_tagged(const void* d_cells16, int64_t n, int unknown_is_filled, const uint32_t* ids,
+                               const uint32_t* kinds, int nq, uint8_t* d_mask, cudaStream_t st);
 
 // Slab (multi-GPU) support for the binary pass: per-line 4-byte summary of one slab, and the resolution of one
 // rank's carries from the all-gathered summaries of every rank (d_all[r*nlines + line], d_widths[r]).
@@ -34,6 +40,13 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
 
 // d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution
 cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st);   // d_dbg: optional 2 x 1024 x 8 phase clocks (diagnostics), or NULL
+
+// add_virtual_border (reference sdf_generation.hpp:287-419): pad the inner mask with a one-cell shell on every axis longer than
+// one cell (ox/oy/oz = 1 or 0), and the per-voxel select between the two padded fields
+cudaError_t launch_border_pad(const uint8_t* d_inner, int64_t nx, int64_t ny, int64_t nz, int ox, int oy, int oz, int shell,
+                              uint8_t* d_padded, cudaStream_t st);
+cudaError_t launch_border_select(const float* d_a, const float* d_b, int64_t nx, int64_t ny, int64_t nz, int ox, int oy, int oz,
+                                 float* d_out, cudaStream_t st);
 
 // Grid-aligned gradient field of an f32 SDF (reference sdf.hpp:341-358 + :432-526): d_grad = 3 values per voxel, f64 or f32
 cudaError_t launch_gradient(const float* d_sdf, int64_t nx, int64_t ny, int64_t nz, double res, int edges, int out_f64,

@@ -184,6 +184,23 @@ def test_pipelined_host_path(ctx):
         assert (mx, mn) == (wmx, wmn)
 
 
+def test_pipelined_cells_path(ctx):
+    """COLLISION_CELL grids >= 2^25 voxels: x-chunks of cells are uploaded into two staging halves used alternately, packed
+    to mask bytes on the device and fed to the same chunked passes (capi.cu build_host_pipelined)."""
+    from sdf_tools_b200.api import COLLISION_CELL_DTYPE
+    occ = synth.octree((320, 320, 336), 0.3, 5)
+    assert occ.size >= 1 << 25
+    cells = np.zeros(occ.shape, dtype=COLLISION_CELL_DTYPE)
+    cells["occupancy"] = occ
+    cells["component"] = 3
+    for unknown in (False, True):
+        mask = O.pack_cells(cells, unknown)
+        want, wmx, wmn = O.build_sdf(mask, 0.02)
+        got, (mx, mn) = ctx.build_from_cells(cells, 0.02, unknown)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert (mx, mn) == (wmx, wmn)
+
+
 # ---------------------------------------------------------------------------- BASELINE.json configs at their stated sizes
 def _mem_gb():
     try:
