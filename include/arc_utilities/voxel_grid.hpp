@@ -65,6 +65,12 @@ protected:
 public:
     VoxelGrid() = default;
     virtual ~VoxelGrid() = default;
+    // the user-declared destructor would otherwise suppress the implicit moves, and "moving" a grid (e.g. the
+    // SignedDistanceField returned by ExtractSignedDistanceField) would copy its whole backing store
+    VoxelGrid(const VoxelGrid&) = default;
+    VoxelGrid& operator=(const VoxelGrid&) = default;
+    VoxelGrid(VoxelGrid&&) = default;
+    VoxelGrid& operator=(VoxelGrid&&) = default;
     // cell-count constructors
     VoxelGrid(const Eigen::Isometry3d& origin, double cell, int64_t nx, int64_t ny, int64_t nz, const T& dflt)
     { Init(origin, cell, cell, cell, nx, ny, nz, dflt, dflt); }

@@ -1,5 +1,7 @@
-"""tools/ab_env.py -- A/B timing of kernel variants selected by environment knobs: each variant runs in its own process
-(the knobs are read once) on the same workloads; prints per-kernel medians and a checksum of the result."""
+"""tools/ab_env.py -- per-kernel timing of the product library on named workloads, optionally against variants selected by
+environment variables (`name:ENV=value,...`; e.g. an alternative library through SDF_B200_LIB): each variant runs in its own
+process on the same workloads; prints per-kernel medians and a checksum of the result.
+  python tools/ab_env.py c3 c5 c4@2048,2048,128 exp:SDF_B200_LIB=/path/to/libvariant.so"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
@@ -31,10 +33,13 @@ for wl in sys.argv[1:]:
     del m, out, ctx
 print(json.dumps(res))
 ''' % ROOT
-variants = [("band+lut (round 1)", {"SDF_B200_HULL": "band", "SDF_B200_SQRT": "lut"}),
-
-]
-wls = sys.argv[1:] or ["c3", "c5", "c2"]
+# name=ENV1=a,ENV2=b ... on the command line adds a variant; without any, the product library is timed as it is
+variants = [("product", {})]
+args = [a for a in sys.argv[1:] if "=" not in a]
+for spec in [a for a in sys.argv[1:] if "=" in a]:
+    name, _, rest = spec.partition(":")
+    variants.append((name, dict(kv.split("=", 1) for kv in rest.split(",") if kv)))
+wls = args or ["c3", "c5", "c2"]
 for name, env in variants:
     r = subprocess.run([sys.executable, "-c", CHILD] + wls, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     print(name, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "FAILED " + r.stderr[-600:], flush=True)
