@@ -156,10 +156,10 @@ class SlabBuilder:
         self._symm = None
         want = os.environ.get("SDF_B200_EXCHANGE", "p2p")
         if world > 1 and parts == 1 and want != "nccl":
+            import torch.distributed as dist
+            grp = group if group is not None else dist.group.WORLD
             try:
-                import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm_mem
-                grp = group if group is not None else dist.group.WORLD
                 # two gather buffers used alternately: build i+1 may store while a slow peer still reads build i
                 buf = symm_mem.empty(2 * self.nslabs * nl, dtype=torch.int32, device=dev)
                 hdl = symm_mem.rendezvous(buf, grp)
@@ -167,10 +167,16 @@ class SlabBuilder:
                 self._symm = hdl
                 self._peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
                 self._parity = 0
-                self.exchange = "p2p"
             except Exception as e:               # no symmetric memory on this build / topology: NCCL all-gather
                 self._symm = None
                 self._symm_error = repr(e)
+            # every rank must take the same path: one that could not set up symmetric memory sends all of them to NCCL
+            agree = torch.tensor([1 if self._symm is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=grp)
+            if int(agree.item()) == 1:
+                self.exchange = "p2p"
+            else:
+                self._symm = None
 
     def alloc_outputs(self):
         torch = self.torch
