@@ -1,13 +1,19 @@
 #!/bin/bash
-# Round-end measurement set (single GPU): bench line, ncu launch list of the same command, counters, one full capture.
+# Round-end measurement set (single GPU): bench line, reference arm, ncu launch list of the bench command, counters,
+# one full capture of the three build kernels, per-phase source counters, traffic file tied to the kernel source hash.
+R=${1:-r2}
 mkdir -p gpurun_out
-timeout 300 python bench.py > gpurun_out/r1_bench_n1.json 2> gpurun_out/r1_bench_n1.err
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1
-timeout 200 tools/ncu_counts.sh
-timeout 240 ncu --set full --clock-control none --import-source on --kernel-name regex:band_strided -c 2 -o gpurun_out/r1_prof -f python tools/one_build.py c3 > gpurun_out/r1_ncu_full.log 2>&1
-python - <<'P'
+timeout 600 python bench.py > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err
+timeout 300 python bench.py --impl reference > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-c4 --no-same-config > gpurun_out/b_ncu.log 2>&1
+timeout 300 tools/ncu_counts.sh
+cp gpurun_out/counts_libsdf_b200.csv gpurun_out/${R}_counters.csv
+timeout 400 ncu --set full --clock-control none --import-source on --kernel-name regex:'binary_z|band_strided' -s 3 -c 3 -o gpurun_out/${R}_prof -f python tools/one_build.py c3 > gpurun_out/${R}_ncu_full.log 2>&1
+nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${R}_gpu.csv
+lscpu | head -20 > gpurun_out/${R}_lscpu.txt
+python - <<P
 import json
-d=json.load(open("gpurun_out/r1_bench_n1.json"))
+d=json.load(open("gpurun_out/${R}_bench_n1.json"))
 print(round(d["value"]), round(d["ms_per_step"],3), round(d["e2e"]["value"]), d["roofline"]["frac"], d["gpu_launches"], d["clocks"])
 P
 ls -la gpurun_out | tail -8

@@ -29,7 +29,7 @@ def main():
     traffic = {}
     print(f"# ncu summary (`ncu --set full --clock-control none --import-source on`, one capture per kernel of one 1024^3 build, B200)\n")
     print(f"Source: {rep} (scratch; regenerate with tools/final_profile.sh + tools/ncu_summary.py).")
-    print("Times under ncu are cold-cache and serialised; bench values come from CUDA events in bench.py (profiles/r1_bench_n1.json).\n")
+    print("Times under ncu are cold-cache and serialised; bench values come from CUDA events in bench.py (profiles/*_bench_n1.json).\n")
     for r in rows[2:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
         name = d["Kernel Name"]
@@ -66,7 +66,15 @@ def main():
             dd = {m: v for m, v, _ in ms}
             if "dram__bytes_read.sum" in dd and name not in traffic:
                 traffic[name] = float(dd["dram__bytes_read.sum"].replace(",", "")) + float(dd["dram__bytes_write.sum"].replace(",", ""))
-    json.dump(traffic, open("/tmp/ncu_traffic.json", "w"), indent=1)
+    # traffic file read by bench.py: only valid for the kernel sources it was measured on (hash)
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import kernel_source_hash
+    out = {"kernel_source_hash": kernel_source_hash(), "grid": "1024x1024x1024", "source": f"{rep} (ncu --set full, one launch per kernel)"}
+    for name, b in traffic.items():
+        key = "pass1_z_ms" if "binary_z" in name else ("pass3_x_ms" if ("(bool)1" in name or ", 1>" in name) else "pass2_y_ms")
+        out[key] = {"kernel": name.split("(")[0], "dram_bytes_per_launch": b}
+    json.dump(out, open("/tmp/ncu_traffic.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -11,6 +11,7 @@ else: mh = synth.make_mask(wl); np.save(cache, mh)
 m = torch.from_numpy(mh).cuda()
 out = torch.empty((nx, ny, nz), dtype=torch.float32, device="cuda")
 ctx = Context(0); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-ctx.build_device(m.data_ptr(), nx, ny, nz, cfg["res"], out.data_ptr())
-torch.cuda.synchronize()
+for _ in range(2):                                   # the second build is the warm one (ncu: -s 3 -c 3 skips the first)
+    ctx.build_device(m.data_ptr(), nx, ny, nz, cfg["res"], out.data_ptr())
+    torch.cuda.synchronize()
 print("ok", ctx.last_timing())
