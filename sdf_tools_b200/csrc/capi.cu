@@ -280,7 +280,7 @@ int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t
         // heights of the envelope passes, exactly as for an unsharded grid
         int64_t total_nz = 0;
         for (int r = 0; r < nranks; ++r) {
-            if (slab_widths[r] < 0) return fail(ctx, SDF_B200_ERR_ARG, "negative slab width");
+            if (slab_widths[r] <= 0) return fail(ctx, SDF_B200_ERR_ARG, "empty slab (every rank must own at least one z plane)");
             total_nz += slab_widths[r];
         }
         if (total_nz > SDF_B200_MAX_AXIS)
