@@ -237,7 +237,7 @@ def run_reference(args):
     }))
 
 
-def time_device_builds(ctx, torch, stream, mask_h, res, steps, warmup):
+def time_device_builds(ctx, torch, stream, mask_h, res, steps, warmup, sampler=None):
     """CUDA-event time of `steps` device-resident builds; returns (ms_per_step, per-pass means, extrema, launches, d_sdf)."""
     nx, ny, nz = mask_h.shape
     d_mask = torch.from_numpy(mask_h).cuda()
@@ -249,6 +249,8 @@ def time_device_builds(ctx, torch, stream, mask_h, res, steps, warmup):
     for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
+    if sampler:
+        sampler.start()                                   # clocks are sampled during the timed builds only
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(steps):
@@ -364,8 +366,7 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     sampler = ClockSampler(0)
-    sampler.start()
-    ms_per_step, means, (mx, mn), launches, d_mask, d_sdf = time_device_builds(ctx, torch, stream, mask_h, res, args.steps, args.warmup)
+    ms_per_step, means, (mx, mn), launches, d_mask, d_sdf = time_device_builds(ctx, torch, stream, mask_h, res, args.steps, args.warmup, sampler)
     clocks = sampler.stop()
     launches *= args.steps
     del d_mask, d_sdf

@@ -43,13 +43,15 @@ def bind_to_gpu_numa_node(local_rank: int):
         return None
 
 
-def time_slab_builds(torch, dist, sb, d_masks, d_sdfs, res, steps, warmup, stream):
+def time_slab_builds(torch, dist, sb, d_masks, d_sdfs, res, steps, warmup, stream, sampler=None):
     def step():
         sb.build(d_masks, res, d_sdfs)
     for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
     dist.barrier()
+    if sampler:
+        sampler.start()                                   # clocks are sampled during the timed builds only
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -90,9 +92,7 @@ def run_multi(args, world: int, rank: int, local_rank: int):
     stream = torch.cuda.current_stream()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_per_step = time_slab_builds(torch, dist, sb, d_masks, d_sdfs, res, args.steps, args.warmup, stream)
+    ms_per_step = time_slab_builds(torch, dist, sb, d_masks, d_sdfs, res, args.steps, args.warmup, stream, sampler)
     per_pass = {k: [] for k in PASS_BYTES}
     ctx.set_stream(stream.cuda_stream)
     for _ in range(min(args.steps, 5)):                  # per-kernel times: build the rank's slabs one by one
