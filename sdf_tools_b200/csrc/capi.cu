@@ -17,7 +17,7 @@ struct sdf_b200_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    int* d_ext = nullptr;              // [0] max +d2 over free voxels, [1] max d2 over filled voxels
+    int* d_ext = nullptr;              // [0] max +d2 over free voxels, [1] max d2 over filled voxels, [2] sticky: a tile copy timed out
     void* d_carries = nullptr; size_t carries_bytes = 0;   // slab builds: int2 per z line
     int* d_widths = nullptr;
     float* d_lut = nullptr;            // (float)(sqrt((double)m)*res) for m < LUT_N at resolution lut_res
@@ -60,6 +60,15 @@ static int fail(sdf_b200_ctx* ctx, int code, const char* what, cudaError_t e = c
 }
 
 #define CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(ctx, SDF_B200_ERR_CUDA, what, _e); } while (0)
+
+// ext[2] != 0: an envelope kernel gave up waiting for its TMA tile copy (the result of that build is garbage)
+static int check_tile_flag(sdf_b200_ctx* ctx, sdf_b200_ctx* owner, int flag)
+{
+    if (!flag) return SDF_B200_OK;
+    cudaSetDevice(owner->device);
+    cudaMemsetAsync(owner->d_ext + 2, 0, sizeof(int), owner->stream);
+    return fail(ctx, SDF_B200_ERR_CUDA, "a TMA tile copy of the envelope pass timed out (result discarded); SDF_B200_TMA=0 selects plain loads");
+}
 
 static int check_dims(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int64_t nz)
 {
@@ -107,7 +116,8 @@ int sdf_b200_create(sdf_b200_ctx** out, int device)
     ctx = new sdf_b200_ctx();
     ctx->device = device;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&ctx->d_ext, 2 * sizeof(int))) != cudaSuccess) {
+        (e = cudaMalloc(&ctx->d_ext, 4 * sizeof(int))) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_ext, 0, 4 * sizeof(int))) != cudaSuccess) {
         fail(nullptr, SDF_B200_ERR_CUDA, "sdf_b200_create: stream/alloc", e);
         delete ctx;
         return SDF_B200_ERR_CUDA;
@@ -336,9 +346,10 @@ int sdf_b200_get_extrema_raw(sdf_b200_ctx* ctx, int32_t* out_max_free_d2, int32_
         return SDF_B200_OK;
     }
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    int h[2] = {0, 0};
+    int h[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
     CK(cudaStreamSynchronize(ctx->stream), "sync");
+    if (int rc = check_tile_flag(ctx, ctx, h[2])) return rc;
     if (out_max_free_d2) *out_max_free_d2 = h[0];
     if (out_max_filled_d2) *out_max_filled_d2 = h[1];
     return SDF_B200_OK;
@@ -359,9 +370,10 @@ int sdf_b200_get_extrema(sdf_b200_ctx* ctx, double* out_max, double* out_min)
     if (!ctx->built) return fail(ctx, SDF_B200_ERR_ARG, "sdf_b200_get_extrema: no finished build on this context");
     if (ctx->peers.size() > 1) return sdf_b200_extrema_from_raw(ctx->raw_ext[0], ctx->raw_ext[1], ctx->res, out_max, out_min);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    int h[2] = {0, 0};
+    int h[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(h, ctx->d_ext, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream), "copy extrema");
     CK(cudaStreamSynchronize(ctx->stream), "sync");
+    if (int rc = check_tile_flag(ctx, ctx, h[2])) return rc;
     const double inf = std::numeric_limits<double>::infinity();
     // distance = sqrt(d2_filled)*res - sqrt(d2_free)*res, one term being 0 (sdf_generation.hpp:254-256);
     // sqrt is monotone, so the extrema of the f64 value sit at the per-polarity maxima of d2.
@@ -535,9 +547,10 @@ static int build_multi_host(sdf_b200_ctx* lead, const void* h_in, bool is_cells,
     for (int r = 0; r < n; ++r) {
         sdf_b200_ctx* p = lead->peers[r];
         CK(cudaSetDevice(p->device), "cudaSetDevice");
-        int h[2] = {0, 0};
+        int h[3] = {0, 0, 0};
         CK(cudaMemcpyAsync(h, p->d_ext, sizeof(h), cudaMemcpyDeviceToHost, p->stream), "copy extrema");
         CK(cudaStreamSynchronize(p->stream), "sync");
+        if (int frc = check_tile_flag(lead, p, h[2])) return frc;
         raw[0] = h[0] > raw[0] ? h[0] : raw[0];
         raw[1] = h[1] > raw[1] ? h[1] : raw[1];
         launches += p->launches + (n > 1 ? 2 : 0) + (is_cells ? 1 : 0);
@@ -899,7 +912,10 @@ int sdf_b200_build_object_sdfs(sdf_b200_ctx* ctx, const void* tagged_cells, int6
     }
     std::vector<int> raw((size_t)nqueries * 2);
     CK(cudaMemcpyAsync(raw.data(), ctx->d_ext_objs, raw.size() * sizeof(int), cudaMemcpyDeviceToHost, st), "copy extrema");
+    int tile_flag = 0;
+    CK(cudaMemcpyAsync(&tile_flag, ctx->d_ext + 2, sizeof(int), cudaMemcpyDeviceToHost, st), "copy flag");
     CK(cudaStreamSynchronize(st), "sync");
+    if ((rc = check_tile_flag(ctx, ctx, tile_flag))) { cudaStreamSynchronize(cs); return rc; }
     CK(cudaStreamSynchronize(cs), "sync copies");
     for (int k = 0; k < nqueries; ++k)
         sdf_b200_extrema_from_raw(raw[2 * k], raw[2 * k + 1], resolution, out_max ? out_max + k : nullptr, out_min ? out_min + k : nullptr);
@@ -950,7 +966,10 @@ int sdf_b200_build_with_border(sdf_b200_ctx* ctx, const uint8_t* mask_free, cons
        "launch border_select");
     ++launches;
     CK(cudaMemcpyAsync(out_sdf, ctx->d_grad, (size_t)N * 4, cudaMemcpyDeviceToHost, st), "D2H sdf");
+    int tile_flag = 0;
+    CK(cudaMemcpyAsync(&tile_flag, ctx->d_ext + 2, sizeof(int), cudaMemcpyDeviceToHost, st), "copy flag");
     CK(cudaStreamSynchronize(st), "sync");
+    if ((rc = check_tile_flag(ctx, ctx, tile_flag))) return rc;
     ctx->launches = launches;
     ctx->last_dims[0] = ctx->last_dims[1] = ctx->last_dims[2] = 0;
     double mx = 0, mn = 0, dummy = 0;
