@@ -9,8 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsdf_b200.so")
-SOURCES = ["edt_kernels.cu", "capi.cu"]
-HEADERS = ["edt_kernels.cuh", "band_hull.cuh", os.path.join("..", "..", "include", "sdf_b200.h")]
+SOURCES = ["edt_kernels.cu", "line_kernels.cu", "capi.cu"]
+HEADERS = ["edt_kernels.cuh", "band_hull.cuh", "line_hull.cuh", os.path.join("..", "..", "include", "sdf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -35,6 +35,10 @@ struct sdf_b200_ctx {
     void* d_grad = nullptr; size_t grad_bytes = 0;  // gradient staging of the host entry point
     void* d_out2 = nullptr; size_t out2_bytes = 0;  // second result buffer of the batched object builds
     int* d_ext_objs = nullptr; size_t ext_objs_n = 0;
+    // scratch of the line-per-thread envelope passes: the field between the y and x passes, the hull stacks, polarity bits
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    void* d_stack = nullptr; size_t stack_bytes = 0;
+    void* d_pol = nullptr; size_t pol_bytes = 0;
     int64_t last_dims[3] = {0, 0, 0};               // grid of the last HOST build whose field is still in d_out
     double res = 1.0;
     bool built = false;
@@ -167,6 +171,9 @@ void sdf_b200_destroy(sdf_b200_ctx* ctx)
     if (ctx->d_grad) cudaFree(ctx->d_grad);
     if (ctx->d_out2) cudaFree(ctx->d_out2);
     if (ctx->d_ext_objs) cudaFree(ctx->d_ext_objs);
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->d_stack) cudaFree(ctx->d_stack);
+    if (ctx->d_pol) cudaFree(ctx->d_pol);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -204,10 +211,56 @@ int sdf_b200_host_free(void* p)
     return SDF_B200_OK;
 }
 
-// mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in place in d_field
+// Which envelope kernel: "line" (one thread per line, hull stacks in an L2-resident scratch field; needs 8-12 extra bytes
+// per voxel) or "band" (in place, stacks in shared memory).  SDF_B200_HULL=band|line overrides; the default is "line",
+// falling back to "band" when the scratch cannot be allocated.
+static int hull_knob()
+{
+    static int knob = -1;
+    if (knob < 0) { const char* e = getenv("SDF_B200_HULL"); knob = (e && e[0] == 'b') ? 0 : 1; }
+    return knob;
+}
+
+static bool line_transposed()
+{
+    static int knob = -1;
+    if (knob < 0) { const char* e = getenv("SDF_B200_LINE_T"); knob = (e && e[0] == '0') ? 0 : 1; }
+    return knob != 0;
+}
+
+struct LinePlan {
+    bool use = false;
+    bool wide_y = false, wide_x = false;   // 64-bit stack entries (line longer than 1024 or heights >= 2^22)
+    int64_t polw_y = 0, polw_x = 0;        // polarity words of one pass
+};
+
+// Decide the kernel for a grid and size the scratch.  nz_total: the whole z extent the binary pass saw (slab builds).
+static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int64_t nz, int64_t nz_total)
+{
+    LinePlan P;
+    if (!hull_knob()) return P;
+    const int64_t N = nx * ny * nz;
+    const int64_t hz = (nz_total - 1) * (nz_total - 1), hy = (ny - 1) * (ny - 1);
+    P.wide_y = ny > 1024 || hz >= (1 << 22);
+    P.wide_x = nx > 1024 || hz + hy >= (1 << 22);
+    P.polw_y = nx * ((ny + 31) / 32) * nz;
+    P.polw_x = ((nx + 31) / 32) * ny * nz;
+    const size_t stack_need = (size_t)N * ((P.wide_y || P.wide_x) ? 8 : 4);
+    const size_t pol_need = (size_t)(P.polw_y > P.polw_x ? P.polw_y : P.polw_x) * 4;
+    char keep[512]; memcpy(keep, ctx->err, sizeof(keep));
+    if (grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)N * 4) || grow(ctx, &ctx->d_stack, &ctx->stack_bytes, stack_need) ||
+        grow(ctx, &ctx->d_pol, &ctx->pol_bytes, pol_need)) {
+        memcpy(ctx->err, keep, sizeof(keep));          // not an error: the in-place kernel needs no scratch
+        return P;
+    }
+    P.use = true;
+    return P;
+}
+
+// mask -> signed int32 d^2 (final_pass = false) or f32 distance (final_pass = true), in d_field
 static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int64_t ny, int64_t nz, double res,
                       int32_t* d_field, bool final_pass, const void* d_carries = nullptr, bool keep_extrema = false,
-                      unsigned mask_bits = 0xffu)
+                      unsigned mask_bits = 0xffu, int64_t nz_total = 0)
 {
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
@@ -221,7 +274,34 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
         ctx->lut_res = res;
         ctx->launches++;
     }
+    const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz_total > 0 ? nz_total : nz);
     CK(cudaEventRecord(ctx->ev[0], st), "event");
+    if (LP.use) {
+        // out of place: z pass -> A, y pass A -> B, x pass B -> A, with A = d_field unless there is no y pass
+        int32_t* tmp = (int32_t*)ctx->d_tmp;
+        int32_t* after_z = ny > 1 ? d_field : tmp;
+        CK(sdfb200::launch_binary_z(d_mask, after_z, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
+        ctx->launches++;
+        CK(cudaEventRecord(ctx->ev[1], st), "event");
+        // the y pass leaves its result with x and y swapped (tmp[y][x][z]): both passes then READ rows that are nz apart
+        // (input and stack of one line stay inside a few pages) and only their stores stride by a whole plane
+        if (ny > 1) {
+            CK(sdfb200::launch_line_hull(d_field, tmp, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz,
+                                         line_transposed() ? nx * nz : nz, line_transposed() ? nz : ny * nz, LP.wide_y, false,
+                                         res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(ctx->ev[2], st), "event");
+        if (line_transposed())
+            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, nz, nz, ny, nx * nz, ny * nz, nz, LP.wide_x,
+                                         final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
+               "launch line_hull(x)");
+        else
+            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, ny * nz, ny * nz, 1, 0, ny * nz, 0, LP.wide_x,
+                                         final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
+               "launch line_hull(x)");
+        ctx->launches++;
+    } else {
     CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
@@ -235,6 +315,7 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
                                     final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
        "launch band_strided(x)");
     ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->ev[3], st), "event");
     ctx->timed = true;
     ctx->built = final_pass;
@@ -310,8 +391,10 @@ int sdf_b200_slab_build_device(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t
            "launch slab_carry");
         carries = ctx->d_carries;
     }
+    int64_t nz_total = 0;
+    for (int r = 0; r < nranks; ++r) nz_total += slab_widths[r];
     rc = run_passes(ctx, d_mask, nx, ny, nz_local, resolution, reinterpret_cast<int32_t*>(d_sdf), true, carries,
-                    keep_extrema != 0);
+                    keep_extrema != 0, 0xffu, nz_total);
     if (rc == SDF_B200_OK && carries) ctx->launches++;
     return rc;
 }
@@ -538,7 +621,7 @@ static int build_multi_host(sdf_b200_ctx* lead, const void* h_in, bool is_cells,
                "launch slab_carry");
             carries = p->d_carries;
         }
-        rc = run_passes(p, (const uint8_t*)p->d_mask, nx, ny, w[r], res, (int32_t*)p->d_out, true, carries, false);
+        rc = run_passes(p, (const uint8_t*)p->d_mask, nx, ny, w[r], res, (int32_t*)p->d_out, true, carries, false, 0xffu, nz);
         if (rc) { if (p != lead) snprintf(lead->err, sizeof(lead->err), "%s", p->err); return rc; }
         CK(cudaMemcpy2DAsync(out_sdf + z0[r], (size_t)nz * 4, p->d_out, (size_t)w[r] * 4, (size_t)w[r] * 4, (size_t)nlines,
                              cudaMemcpyDeviceToHost, st), "D2H sdf slab");
@@ -617,6 +700,9 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     uint8_t* d_mask = (uint8_t*)ctx->d_mask;
     int32_t* d_field = (int32_t*)ctx->d_out;
+    const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz);
+    int32_t* tmp = (int32_t*)ctx->d_tmp;
+    const int64_t nwy = (ny + 31) / 32, nwx = (nx + 31) / 32;
     ctx->launches = 0;
     ctx->timed = false;
     CK(cudaMemsetAsync(ctx->d_ext, 0, 2 * sizeof(int), st), "memset extrema");
@@ -648,7 +734,13 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         }
         CK(sdfb200::launch_binary_z(d_mask + off, d_field + off, (int)nz, (x1 - x0) * ny, nullptr, st), "launch binary_z");
         ctx->launches++;
-        if (ny > 1) {
+        if (ny > 1 && LP.use) {     // x-chunk of the y pass: reads field[x0..x1), writes tmp[y][x0..x1)[z]
+            CK(sdfb200::launch_line_hull(d_field + off, tmp + (line_transposed() ? x0 * nz : off), (char*)ctx->d_stack + (size_t)off * (LP.wide_y ? 8 : 4),
+                                         (uint32_t*)ctx->d_pol + x0 * nwy * nz, (int)ny, nz, nz, x1 - x0, plane,
+                                         line_transposed() ? nx * nz : nz, line_transposed() ? nz : plane, LP.wide_y, false, res, ctx->d_ext,
+                                         nullptr, 0, st), "launch line_hull(y)");
+            ctx->launches++;
+        } else if (ny > 1) {
             CK(sdfb200::launch_band_strided(d_field + off, (int)ny, nz, nz, x1 - x0, plane, false, res, ctx->d_ext, nullptr,
                                             nullptr, 0, st), "launch band_strided(y)");
             ctx->launches++;
@@ -658,8 +750,17 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         const int64_t y0 = ny * j / NCH, y1 = ny * (j + 1) / NCH;
         if (y1 == y0) continue;
         const int64_t col0 = y0 * nz, ncols = (y1 - y0) * nz;
-        CK(sdfb200::launch_band_strided(d_field + col0, (int)nx, plane, ncols, 1, 0, true, res, ctx->d_ext, nullptr,
-                                        ctx->d_lut, LUT_N, st), "launch band_strided(x)");
+        if (LP.use && line_transposed())      // y-chunk of the x pass: reads tmp[y0..y1), writes field[.][y0..y1)[z]
+            CK(sdfb200::launch_line_hull(tmp + y0 * nx * nz, d_field + col0, (char*)ctx->d_stack + (size_t)(y0 * nx * nz) * (LP.wide_x ? 8 : 4),
+                                         (uint32_t*)ctx->d_pol + y0 * nwx * nz, (int)nx, nz, nz, y1 - y0, nx * nz, plane, nz, LP.wide_x, true,
+                                         res, ctx->d_ext, ctx->d_lut, LUT_N, st), "launch line_hull(x)");
+        else if (LP.use)
+            CK(sdfb200::launch_line_hull(tmp + col0, d_field + col0, (char*)ctx->d_stack + (size_t)col0 * (LP.wide_x ? 8 : 4), (uint32_t*)ctx->d_pol + col0 * nwx,
+                                         (int)nx, plane, ncols, 1, 0, plane, 0, LP.wide_x, true, res, ctx->d_ext, ctx->d_lut, LUT_N, st),
+               "launch line_hull(x)");
+        else
+            CK(sdfb200::launch_band_strided(d_field + col0, (int)nx, plane, ncols, 1, 0, true, res, ctx->d_ext, nullptr,
+                                            ctx->d_lut, LUT_N, st), "launch band_strided(x)");
         ctx->launches++;
         CK(cudaEventRecord(ctx->chunk_ev[8 + j], st), "event");
         CK(cudaStreamWaitEvent(cs, ctx->chunk_ev[8 + j], 0), "wait");

@@ -38,6 +38,15 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
                                 int64_t outer_stride, bool final_pass, double res, int* d_ext, long long* d_dbg,
                                 const float* d_lut, int lut_n, cudaStream_t st);
 
+// K2/K3, line-per-thread variant (line_kernels.cu): OUT OF PLACE.  Line (outer, col), col < ncols contiguous:
+//        input position y at in[outer*outer_stride + col + y*line_stride], result at out[outer*out_outer_stride + col +
+//        y*out_stride] (so a pass can also re-order the axes), hull stack in d_stack with the addressing of the input
+//        (one entry per voxel: 4 bytes, or 8 with wide_entries -- required when n > 1024 or a height can reach 2^22),
+//        one polarity bit per voxel in d_pol (nouter x ceil(n/32) x ncols words).
+cudaError_t launch_line_hull(const int32_t* in, void* out, void* d_stack, uint32_t* d_pol, int n, int64_t line_stride, int64_t ncols,
+                             int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, bool wide_entries,
+                             bool final_pass, double res, int* d_ext, const float* d_lut, int lut_n, cudaStream_t st);
+
 // d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution
 cudaError_t launch_sqrt_lut(float* d_lut, int n, double res, cudaStream_t st);   // d_dbg: optional 2 x 1024 x 8 phase clocks (diagnostics), or NULL
 

@@ -1,0 +1,294 @@
+// sdf_tools_b200/csrc/line_hull.cuh
+//
+// One 1-D pass of the signed-fused exact Euclidean distance transform along a STRIDED axis, ONE THREAD PER LINE:
+// the inner work of sdf_generation::BuildDistanceField (/root/reference/include/sdf_tools/sdf_generation.hpp:95-207,
+// called twice at :242-243) for one axis.  The 32 lanes of a warp own 32 ADJACENT lines, so every row of the field is
+// read and written as one 128-byte access; each thread runs the classic sequential lower-envelope algorithm
+// (Felzenszwalb / Meijster) over its whole line: a build sweep that keeps the hull of the lifted points as a stack, then a
+// query sweep that walks the stack.  No bands, no seam merges, no block-wide barriers, no shared memory.
+//
+// The stack does not fit on chip (up to n entries per line), so it lives in a global scratch field with the SAME
+// [row][line] layout as the data: the entries at depth k of 32 adjacent lines share a 128-byte row.  Adjacent lines have
+// similar hulls, so the pushes / pops / reads of a warp touch a handful of rows that stay in the (126 MB) L2; only the
+// long-lived part of a stack can spill to HBM (at most one write and one read of the final hull: <= 0.3 entries per voxel).
+//
+// Signed-fused field: s > 0 <=> voxel FREE, s = d^2 to the nearest FILLED; s < 0 <=> voxel FILLED, -s = d^2 to the
+// nearest FREE (partial over the axes done so far; |s| == SDF_INF: other polarity not seen yet).  Along a line the two
+// transforms decouple into maximal RUNS [a,e) of equal polarity; inside a run the candidates are the run's finite
+// positions (q, |s(q)|) plus the two BOUNDARY SITES (a-1, 0) and (e, 0) -- the nearest voxels of the other polarity.
+// They are ordinary hull points: the left one is the bottom of the run's chain, the right one closes the chain (pops
+// what it hides) when the run ends.  The query sweep then needs two candidate values and one comparison per position.
+//
+// Scratch layout.  The hull of run [a,e) occupies the stack rows a, a+1, .. (at most e-a of them: one per vertex, in
+// position order), followed by a terminator when there is room; runs never share rows.  The polarity of every position
+// goes to a bit field pol[word][line] (1/32 of the field), which the query sweep reads to find run ends and signs.
+//
+// Exactness: all integer; hull tests are cross-multiplied in int64 (|dY| < 2^25, |dq| < 2^11).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SDF_HD __host__ __device__ __forceinline__
+#else
+#define SDF_HD inline
+#endif
+
+#ifndef SDF_INF
+#define SDF_INF 0x40000000
+#endif
+
+namespace sdfb200 {
+
+#if defined(LH_COUNT) && !defined(__CUDA_ARCH__)
+#define LH_TICK(x) (++lh_counters[x])
+static long long lh_counters[8];   // 0 sites, 1 finite, 2 pops, 3 runs, 4 query advances
+#else
+#define LH_TICK(x) ((void)0)
+#endif
+
+// Stack entries: 32 bits {position : 10, height : 22} when the line has <= 1024 positions and heights stay below 2^22,
+// else 64 bits {position, height}.
+template <bool WIDE> struct LineEntry;
+template <> struct LineEntry<false> {
+    typedef uint32_t type;
+    static constexpr uint32_t TERM = 0xffffffffu;
+    static SDF_HD type pack(int pos, int32_t h) { return ((uint32_t)pos << 22) | (uint32_t)h; }
+    static SDF_HD bool is_term(type e) { return e == TERM; }
+    static SDF_HD bool is_special(type e) { return e >= 0xfffffffeu; }     // terminator or "not copied yet" marker
+    static SDF_HD type term() { return TERM; }
+    static SDF_HD type empty() { return 0xfffffffeu; }
+    static SDF_HD int pos(type e) { return (int)(e >> 22); }
+    static SDF_HD int32_t h(type e) { return (int32_t)(e & 0x3fffffu); }
+};
+template <> struct LineEntry<true> {
+    typedef unsigned long long type;
+    static SDF_HD type pack(int pos, int32_t h) { return ((unsigned long long)(uint32_t)pos << 32) | (uint32_t)h; }
+    static SDF_HD bool is_term(type e) { return (e >> 32) == 0xffffffffull; }
+    static SDF_HD bool is_special(type e) { return (e >> 32) >= 0xfffffffeull; }
+    static SDF_HD type term() { return 0xffffffff00000000ull; }
+    static SDF_HD type empty() { return 0xfffffffe00000000ull; }
+    static SDF_HD int pos(type e) { return (int)(e >> 32); }
+    static SDF_HD int32_t h(type e) { return (int32_t)(e & 0xffffffffull); }
+};
+
+// t on or above the chord s->u of the lifted points  <=>  parabola t never wins
+SDF_HD bool lh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t uY) {
+    const long long lhs = (long long)(tY - sY) * (long long)(up - tp);
+    const long long rhs = (long long)(uY - tY) * (long long)(tp - sp);
+    return lhs >= rhs;
+}
+
+#if defined(__CUDA_ARCH__)
+#define LH_LDCS(p) __ldcs(p)        // streamed once: evict-first, so the stack rows keep their place in L2
+#define LH_CTZ(x) (__ffs((int)(x)) - 1)
+#else
+#define LH_LDCS(p) (*(p))
+#define LH_CTZ(x) __builtin_ctz(x)
+#endif
+
+// Per-thread scratch of one line pass: 8 entry slots (a ring indexed modulo 8), private to the thread.
+//   build sweep : a write-through copy of the top of the stack (slot = depth index), so pops read shared memory;
+//   query sweep : a FIFO of hull entries copied ahead of the walk with asynchronous global->shared copies.
+// The host stand-in applies asynchronous copies only at wait(), so a read that does not wait for its copy fails tests.
+template <bool WIDE> struct HostLineMem {
+    typedef typename LineEntry<WIDE>::type ent_t;
+    ent_t slot[8]; ent_t pend_val[8]; int pend_k[8]; int npend = 0;
+    void ring_st(int k, ent_t e) { slot[k & 7] = e; }
+    ent_t ring_ld(int k) const { return slot[k & 7]; }
+    void fifo_issue(int k, const ent_t* src) { pend_k[npend] = k & 7; pend_val[npend] = *src; ++npend; }
+    void fifo_commit() {}
+    void fifo_landed_hint() { fifo_wait(); }          // host only: copies issued a block ago have landed by now
+    void fifo_wait() { for (int i = 0; i < npend; ++i) slot[pend_k[i]] = pend_val[i]; npend = 0; }
+    ent_t fifo_ld(int k) const { return slot[k & 7]; }
+};
+
+// One line.  in / stk: element 0 of the line, consecutive positions `stride` elements apart (stk in entries);
+// pol: word 0 of the line's polarity bits, consecutive words `pstride` elements apart.  emit(k, m, neg) receives the
+// squared distance m (<= SDF_INF) and the polarity of positions 0, 1, .. n-1 in order, k = position modulo 8;
+// flush(cnt) follows every 8 positions (cnt = 8) and the last cnt < 8 of the line: the caller may batch its stores there.
+//
+// Chain of a run [a,e), bottom to top:  B, v0, v1, ..  with B the left boundary site (a-1, 0) -- for a = 0 the site
+// (-1, 2^30), which can never win and so stands for "nothing on the left".  Only the vertices v_i are stored (slot a+i).
+// The build keeps the top three elements in registers (T, S unpacked; R = v_{d-3} as a packed entry) and the top eight
+// also in the thread's ring, so a pop normally costs one shared-memory read that is not needed before the next pop.
+template <bool WIDE, typename Mem, typename Emit, typename Flush>
+SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n, typename LineEntry<WIDE>::type* __restrict__ stk,
+                           uint32_t* __restrict__ pol, int64_t pstride, Mem& mem, Emit emit, Flush flush)
+{
+    typedef LineEntry<WIDE> E;
+    typedef typename E::type ent_t;
+    constexpr int32_t BIG = 0x40000000;              // height of the "nothing on the left" boundary site
+    constexpr int32_t NOSITE = 0x60000000;           // height of a non-existent next point: never wins
+    constexpr int K = 8;                             // ring slots
+    if (n <= 0) return;
+    // ------------------------------------------------------------------------------------------------ build sweep
+    {
+        int a = 0, d = 0;                            // current run start; number of vertices on its stack
+        int lo = 0;                                  // ring slots hold v_i for lo <= i < d
+        int bpos = -1; int32_t bY = 1 + BIG;         // left boundary site of the run (lifted height)
+        int tp = bpos; int32_t tY = bY;              // T: top of the chain
+        int sp = tp; int32_t sY = tY + 1;            // S: below T, or the none-sentinel (sp == tp: the hull test is false)
+        ent_t R = 0;                                 // v_{d-3} when it exists
+        ent_t* top = stk;                            // slot a + d
+        const int64_t stride3 = 3 * stride;
+        bool prevpol = in[0] < 0;
+        auto pop_against = [&](int qp, int32_t qY) {
+            while (lh_dominated(sp, sY, tp, tY, qp, qY)) {
+                LH_TICK(2);
+                --d;
+                top -= stride;
+                lo = lo < d ? lo : d;
+                tp = sp; tY = sY;
+                if (d >= 2) {
+                    sp = E::pos(R); sY = sp * sp + E::h(R);                  // v_{d-2}
+                    if (d - 3 >= lo) R = mem.ring_ld(d - 3);                 // v_{d-3}
+                    else if (d >= 3) { LH_TICK(5); R = *(top - stride3); }
+                } else if (d == 1) { sp = bpos; sY = bY; }
+                else { sp = tp; sY = tY + 1; }                               // T is the boundary site: nothing below
+            }
+        };
+        auto row = [&](int y, int32_t v, bool p) {
+            LH_TICK(0);
+            if (p != prevpol) {                      // a run ends at y-1 and the next starts at y
+                LH_TICK(3);
+                pop_against(y, y * y);               // close against the right boundary site (y, 0)
+                if (d < y - a) *top = E::term();
+                a = y; d = 0; lo = 0;
+                bpos = y - 1; bY = bpos * bpos;
+                tp = bpos; tY = bY; sp = tp; sY = tY + 1;
+                top = stk + (int64_t)y * stride;
+                prevpol = p;
+            }
+            const int32_t h = p ? -v : v;
+            if (h < SDF_INF) {
+                LH_TICK(1);
+                const int32_t Y = y * y + h;
+                pop_against(y, Y);
+                const ent_t en = E::pack(y, h);
+                *top = en;
+                mem.ring_st(d, en);
+                top += stride;
+                ++d;
+                lo = lo > d - K ? lo : d - K;
+                R = E::pack(sp, sY - sp * sp);       // (garbage when S is not a vertex: then never used)
+                sp = tp; sY = tY;
+                tp = y; tY = Y;
+            }
+        };
+        constexpr int U = 4;                         // rows read ahead of the (data-dependent) stack work
+        const int32_t* ip = in;
+        uint32_t* pp = pol;
+        uint32_t pw = 0;
+        int32_t vnx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { vnx[u] = (u < n) ? LH_LDCS(ip) : 0; ip += stride; }
+        int y0 = 0;
+        for (; y0 + 2 * U <= n; y0 += U) {           // whole groups with a whole group to read ahead: no bounds checks
+            int32_t vin[U];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vin[u] = vnx[u]; bits |= ((uint32_t)vin[u] >> 31) << u; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vnx[u] = LH_LDCS(ip); ip += stride; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) row(y0 + u, vin[u], (bits >> u) & 1u);
+            pw |= bits << (y0 & 31);
+            if ((y0 & 31) == 32 - U) { *pp = pw; pp += pstride; pw = 0; }
+        }
+        for (; y0 < n; y0 += U) {                    // the last one or two groups
+            int32_t vin[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) vin[u] = vnx[u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vnx[u] = (y0 + U + u < n) ? LH_LDCS(ip) : 0; ip += stride; }
+            for (int u = 0; u < U && y0 + u < n; ++u) {
+                const bool p = vin[u] < 0;
+                row(y0 + u, vin[u], p);
+                pw |= (uint32_t)p << ((y0 + u) & 31);
+            }
+            if ((y0 & 31) == 32 - U || y0 + U >= n) { *pp = pw; pp += pstride; pw = 0; }
+        }
+        if (d < n - a) *top = E::term();             // the last run has no right boundary site
+    }
+    // ------------------------------------------------------------------------------------------------ query sweep
+    {
+        int e = 0;                                   // end of the current run (the first run starts at 0)
+        int cpos = 0, npos = 0;                      // current / next point of the run's hull (vertex or boundary site)
+        int32_t ch = BIG, nh = NOSITE;
+        // FIFO of the run's stack entries in the ring: fi copies issued, ci consumed (slot = count modulo 8); cnt = slots
+        // the run owns (e - a); gp = address of the next slot to copy.  A consumed slot is overwritten with the "empty"
+        // marker, so a read that runs ahead of its copy sees the marker and takes the slow path: no landing bookkeeping.
+        int fi = 0, ci = 0, cnt = 0;
+        const ent_t* gp = stk;
+        bool tail = true, neg = false, ended = true; // ended: the terminator was consumed (nothing more to copy)
+        auto top_up = [&]() {                        // copy ahead until the FIFO is full or the run's slots are exhausted
+            mem.fifo_landed_hint();
+            int want = K - (fi - ci);
+            want = want < cnt - fi ? want : cnt - fi;
+            if (ended) want = 0;
+            for (; want > 0; --want) { mem.fifo_issue(fi, gp); gp += stride; ++fi; }
+            mem.fifo_commit();
+        };
+        // the rare cases of advance(): entry not copied yet, terminator, run exhausted, or already past the last point
+        auto advance_slow = [&](ent_t en) {
+            nh = NOSITE;
+            if (tail) return;
+            if (!E::is_term(en) && ci < cnt) {       // starved: burst of advances, or the run just started
+                LH_TICK(6);
+                if (fi == ci) top_up();
+                mem.fifo_wait();
+                en = mem.fifo_ld(ci);
+                if (!E::is_term(en)) { mem.ring_st(ci, E::empty()); ++ci; npos = E::pos(en); nh = E::h(en); return; }
+            }
+            ended = true; tail = true; npos = e; nh = (e < n) ? 0 : NOSITE;
+        };
+        // next <- the point after it: the following stack entry, then the right boundary site (e, 0), then nothing
+        auto advance = [&]() {
+            cpos = npos; ch = nh;
+            const ent_t en = mem.fifo_ld(ci);
+            if (!E::is_special(en)) { mem.ring_st(ci, E::empty()); ++ci; npos = E::pos(en); nh = E::h(en); }
+            else advance_slow(en);
+        };
+        const uint32_t* pp = pol;
+        const int nw = (n + 31) >> 5;
+        for (int w = 0; w < nw; ++w) {
+            const uint32_t pw = *pp; pp += pstride;
+            const int yend = (w + 1) * 32 < n ? (w + 1) * 32 : n;
+            for (int yb = w * 32; yb < yend; yb += K) {
+                top_up();                            // block of 8 positions: refill what the previous block consumed
+                const int ye = yb + K < yend ? yb + K : yend;
+                for (int y = yb; y < ye; ++y) {
+                    if (y == e) {                    // a run starts here: find its end, restart the walk
+                        neg = (pw >> (y & 31)) & 1u;
+                        uint32_t x = (neg ? ~pw : pw) & ~((2u << (y & 31)) - 1u);      // later positions of the other polarity
+                        int w2 = w;
+                        const uint32_t* p2 = pp;
+                        while (!x && ++w2 < nw) { const uint32_t q = *p2; p2 += pstride; x = neg ? ~q : q; }
+                        e = x ? (w2 << 5) + LH_CTZ(x) : n;
+                        if (e > n) e = n;            // (the bits past the end of the line are zero)
+                        mem.fifo_wait();             // copies of the previous run still in flight must not land later
+#pragma unroll
+                        for (int k = 0; k < K; ++k) mem.ring_st(k, E::empty());
+                        gp = stk + (int64_t)y * stride;
+                        cnt = e - y; fi = 0; ci = 0; ended = false; tail = false;
+                        npos = y - 1; nh = y > 0 ? 0 : BIG;   // the left boundary site becomes `current` ...
+                        advance();                   // ... and the first vertex (or the right boundary site) `next`
+                    }
+                    for (;;) {
+                        const int dc = y - cpos, dn = y - npos;
+                        const int32_t vc = dc * dc + ch, vn = dn * dn + nh;
+                        if (vn > vc) {
+                            emit(y - yb, vc < SDF_INF ? vc : (int32_t)SDF_INF, neg);
+                            break;
+                        }
+                        LH_TICK(4);
+                        advance();
+                    }
+                }
+                flush(ye - yb);
+            }
+        }
+    }
+}
+
+}  // namespace sdfb200
