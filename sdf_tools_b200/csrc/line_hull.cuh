@@ -123,40 +123,45 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
     if (n <= 0) return;
     // ------------------------------------------------------------------------------------------------ build sweep
     {
-        int a = 0, d = 0;                            // current run start; number of vertices on its stack
-        int lo = 0;                                  // ring slots hold v_i for lo <= i < d
+        // Write-back ring: the vertices v_i, lo <= i < d, exist ONLY in the thread's ring (slot i modulo 8); those below
+        // lo are in the global stack.  A push into a full ring first moves v_lo out to global memory; a vertex popped
+        // while still in the ring never costs a global store.  The ring is written out when its run ends.
+        int a = 0, d = 0, lo = 0;                    // current run start; vertices on its stack; first ring-resident one
         int bpos = -1; int32_t bY = 1 + BIG;         // left boundary site of the run (lifted height)
         int tp = bpos; int32_t tY = bY;              // T: top of the chain
         int sp = tp; int32_t sY = tY + 1;            // S: below T, or the none-sentinel (sp == tp: the hull test is false)
         ent_t R = 0;                                 // v_{d-3} when it exists
-        ent_t* top = stk;                            // slot a + d
-        const int64_t stride3 = 3 * stride;
+        ent_t* lop = stk;                            // global slot a + lo
         bool prevpol = in[0] < 0;
         auto pop_against = [&](int qp, int32_t qY) {
             while (lh_dominated(sp, sY, tp, tY, qp, qY)) {
                 LH_TICK(2);
                 --d;
-                top -= stride;
-                lo = lo < d ? lo : d;
+                if (d < lo) { lo = d; lop -= stride; }                       // the popped vertex was already in global memory
                 tp = sp; tY = sY;
                 if (d >= 2) {
                     sp = E::pos(R); sY = sp * sp + E::h(R);                  // v_{d-2}
                     if (d - 3 >= lo) R = mem.ring_ld(d - 3);                 // v_{d-3}
-                    else if (d >= 3) { LH_TICK(5); R = *(top - stride3); }
+                    else if (d >= 3) { LH_TICK(5); R = *(lop - (int64_t)(lo - (d - 3)) * stride); }
                 } else if (d == 1) { sp = bpos; sY = bY; }
                 else { sp = tp; sY = tY + 1; }                               // T is the boundary site: nothing below
             }
+        };
+        auto write_out = [&](int e) {                // the run [a, e) is complete: ring -> global, then the terminator
+            ent_t* q = lop;
+            for (int i = lo; i < d; ++i) { *q = mem.ring_ld(i); q += stride; }
+            if (d < e - a) *q = E::term();
         };
         auto row = [&](int y, int32_t v, bool p) {
             LH_TICK(0);
             if (p != prevpol) {                      // a run ends at y-1 and the next starts at y
                 LH_TICK(3);
                 pop_against(y, y * y);               // close against the right boundary site (y, 0)
-                if (d < y - a) *top = E::term();
+                write_out(y);
                 a = y; d = 0; lo = 0;
                 bpos = y - 1; bY = bpos * bpos;
                 tp = bpos; tY = bY; sp = tp; sY = tY + 1;
-                top = stk + (int64_t)y * stride;
+                lop = stk + (int64_t)y * stride;
                 prevpol = p;
             }
             const int32_t h = p ? -v : v;
@@ -164,51 +169,29 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 LH_TICK(1);
                 const int32_t Y = y * y + h;
                 pop_against(y, Y);
-                const ent_t en = E::pack(y, h);
-                *top = en;
-                mem.ring_st(d, en);
-                top += stride;
+                if (d - lo == K) { *lop = mem.ring_ld(lo); lop += stride; ++lo; }    // ring full: its oldest vertex moves out
+                mem.ring_st(d, E::pack(y, h));
                 ++d;
-                lo = lo > d - K ? lo : d - K;
                 R = E::pack(sp, sY - sp * sp);       // (garbage when S is not a vertex: then never used)
                 sp = tp; sY = tY;
                 tp = y; tY = Y;
             }
         };
-        constexpr int U = 4;                         // rows read ahead of the (data-dependent) stack work
+        // one row per iteration (a single copy of the row code keeps the kernel inside the instruction cache); the
+        // next row's value is requested a whole row of work ahead
         const int32_t* ip = in;
         uint32_t* pp = pol;
         uint32_t pw = 0;
-        int32_t vnx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { vnx[u] = (u < n) ? LH_LDCS(ip) : 0; ip += stride; }
-        int y0 = 0;
-        for (; y0 + 2 * U <= n; y0 += U) {           // whole groups with a whole group to read ahead: no bounds checks
-            int32_t vin[U];
-            uint32_t bits = 0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) { vin[u] = vnx[u]; bits |= ((uint32_t)vin[u] >> 31) << u; }
-#pragma unroll
-            for (int u = 0; u < U; ++u) { vnx[u] = LH_LDCS(ip); ip += stride; }
-#pragma unroll
-            for (int u = 0; u < U; ++u) row(y0 + u, vin[u], (bits >> u) & 1u);
-            pw |= bits << (y0 & 31);
-            if ((y0 & 31) == 32 - U) { *pp = pw; pp += pstride; pw = 0; }
+        int32_t vnext = LH_LDCS(ip); ip += stride;
+        for (int y = 0; y < n; ++y) {
+            const int32_t v = vnext;
+            if (y + 1 < n) { vnext = LH_LDCS(ip); ip += stride; }
+            const bool p = v < 0;
+            row(y, v, p);
+            pw |= (uint32_t)p << (y & 31);
+            if ((y & 31) == 31 || y == n - 1) { *pp = pw; pp += pstride; pw = 0; }
         }
-        for (; y0 < n; y0 += U) {                    // the last one or two groups
-            int32_t vin[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) vin[u] = vnx[u];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { vnx[u] = (y0 + U + u < n) ? LH_LDCS(ip) : 0; ip += stride; }
-            for (int u = 0; u < U && y0 + u < n; ++u) {
-                const bool p = vin[u] < 0;
-                row(y0 + u, vin[u], p);
-                pw |= (uint32_t)p << ((y0 + u) & 31);
-            }
-            if ((y0 & 31) == 32 - U || y0 + U >= n) { *pp = pw; pp += pstride; pw = 0; }
-        }
-        if (d < n - a) *top = E::term();             // the last run has no right boundary site
+        write_out(n);                                // the last run has no right boundary site
     }
     // ------------------------------------------------------------------------------------------------ query sweep
     {

@@ -31,7 +31,7 @@ template <bool WIDE, int TPB> struct DevLineMem {
 };
 
 template <bool WIDE, bool FINAL, int TPB>
-__global__ void __launch_bounds__(TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+__global__ void __launch_bounds__(TPB, 1024 / TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
                                                         typename LineEntry<WIDE>::type* __restrict__ stk, uint32_t* __restrict__ pol,
                                                         int n, int64_t line_stride, int64_t ncols, int64_t nlines, int64_t outer_stride,
                                                         int64_t out_stride, int64_t out_outer_stride,
