@@ -69,6 +69,16 @@ const char* sdf_b200_exchange_kind(const sdf_b200_ctx* ctx); /* "none" | "p2p" |
 int sdf_b200_set_stream(sdf_b200_ctx* ctx, void* cuda_stream, int use_own_stream);
 int sdf_b200_synchronize(sdf_b200_ctx* ctx);
 
+/* Kernels of the two strided envelope passes (the per-axis loops of BuildDistanceField, sdf_generation.hpp:95-207; no
+ * counterpart in the reference -- results are identical in every mode):
+ *   0 auto  : mixed for grids whose y pass has >= 2^20 lines of >= 512 voxels, else band (default; the environment
+ *             variable SDF_B200_HULL=band|line|mixed|auto changes the default of contexts that never call this);
+ *   1 band  : in-place banded kernel, hull stacks in shared memory, no scratch;
+ *   2 line  : one thread per line for both passes, hull stacks in a device scratch (8-12 extra bytes per voxel);
+ *   3 mixed : line-per-thread y pass, banded x pass (4-12 extra bytes per voxel).
+ * Modes that need scratch fall back to band when it cannot be allocated. */
+int sdf_b200_set_envelope_kernel(sdf_b200_ctx* ctx, int mode);
+
 /* Pinned host buffers for the host-side entry points (optional; any host pointer works, pinned is faster). */
 int sdf_b200_host_alloc(void** out, size_t bytes);
 int sdf_b200_host_free(void* p);

@@ -25,6 +25,7 @@ SYMBOLS = [
     ("sdf_b200_last_error", C.c_char_p, [_vp]),
     ("sdf_b200_set_stream", _int, [_vp, _vp, _int]),
     ("sdf_b200_synchronize", _int, [_vp]),
+    ("sdf_b200_set_envelope_kernel", _int, [_vp, _int]),
     ("sdf_b200_host_alloc", _int, [C.POINTER(_vp), C.c_size_t]),
     ("sdf_b200_host_free", _int, [_vp]),
     ("sdf_b200_build_from_mask", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _vp, _pd, _pd]),

@@ -215,6 +215,13 @@ class Context:
     def synchronize(self):
         self._check(self._lib.sdf_b200_synchronize(self._h))
 
+    ENVELOPE_KERNELS = {"auto": 0, "band": 1, "line": 2, "mixed": 3}
+
+    def set_envelope_kernel(self, mode):
+        """Kernels of the two strided envelope passes: "auto" (default), "band", "line" or "mixed" (sdf_b200.h); the
+        result is identical in every mode."""
+        self._check(self._lib.sdf_b200_set_envelope_kernel(self._h, self.ENVELOPE_KERNELS[mode] if isinstance(mode, str) else int(mode)))
+
     def last_timing(self):
         arr = (C.c_float * 4)()
         self._check(self._lib.sdf_b200_last_timing(self._h, arr))

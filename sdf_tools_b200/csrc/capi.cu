@@ -35,6 +35,7 @@ struct sdf_b200_ctx {
     void* d_grad = nullptr; size_t grad_bytes = 0;  // gradient staging of the host entry point
     void* d_out2 = nullptr; size_t out2_bytes = 0;  // second result buffer of the batched object builds
     int* d_ext_objs = nullptr; size_t ext_objs_n = 0;
+    int hull_mode = -1;                             // -1: SDF_B200_HULL default; else HULL_AUTO / BAND / LINE / MIXED (sdf_b200_set_envelope_kernel)
     // scratch of the line-per-thread envelope passes: the field between the y and x passes, the hull stacks, polarity bits
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     void* d_stack = nullptr; size_t stack_bytes = 0;
@@ -211,49 +212,61 @@ int sdf_b200_host_free(void* p)
     return SDF_B200_OK;
 }
 
-// Which envelope kernel: "line" (one thread per line, hull stacks in an L2-resident scratch field; needs 8-12 extra bytes
-// per voxel) or "band" (in place, stacks in shared memory).  SDF_B200_HULL=band|line overrides; the default is "line",
-// falling back to "band" when the scratch cannot be allocated.
-static int hull_knob()
+// Which envelope kernels (sdf_b200_set_envelope_kernel; SDF_B200_HULL=auto|band|line|mixed sets the default of new contexts):
+//   band  : both strided passes with the in-place banded kernel (stacks in shared memory, no scratch);
+//   line  : both passes with the line-per-thread kernel (hull stacks in an L2-resident scratch field; 8-12 extra bytes
+//           per voxel); the y pass leaves its result x/y-swapped so that both passes read rows that are nz apart;
+//   mixed : line-per-thread y pass, banded x pass;
+//   auto  : mixed when one launch of the y pass has at least 2^19 lines of 512..1024 voxels with 32-bit stack entries
+//           (measured: with fewer or shorter lines the line kernel cannot fill the GPU with independent work, and with
+//           64-bit entries its stack traffic doubles -- the banded kernel is faster there), else band.
+// A plan that needs scratch falls back to band when the scratch cannot be allocated.
+enum { HULL_AUTO = 0, HULL_BAND = 1, HULL_LINE = 2, HULL_MIXED = 3 };
+
+static int hull_default()
 {
     static int knob = -1;
-    if (knob < 0) { const char* e = getenv("SDF_B200_HULL"); knob = (e && e[0] == 'b') ? 0 : 1; }
+    if (knob < 0) {
+        const char* e = getenv("SDF_B200_HULL");
+        knob = HULL_AUTO;
+        if (e && e[0] == 'b') knob = HULL_BAND;
+        else if (e && e[0] == 'l') knob = HULL_LINE;
+        else if (e && e[0] == 'm') knob = HULL_MIXED;
+    }
     return knob;
 }
 
-static bool line_transposed()
-{
-    static int knob = -1;
-    if (knob < 0) { const char* e = getenv("SDF_B200_LINE_T"); knob = (e && e[0] == '0') ? 0 : 1; }
-    return knob != 0;
-}
-
 struct LinePlan {
-    bool use = false;
+    int mode = HULL_BAND;                  // resolved: HULL_BAND, HULL_LINE or HULL_MIXED
     bool wide_y = false, wide_x = false;   // 64-bit stack entries (line longer than 1024 or heights >= 2^22)
-    int64_t polw_y = 0, polw_x = 0;        // polarity words of one pass
 };
 
-// Decide the kernel for a grid and size the scratch.  nz_total: the whole z extent the binary pass saw (slab builds).
-static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int64_t nz, int64_t nz_total)
+// Decide the kernels for a grid and size the scratch.  nz_total: the whole z extent the binary pass saw (slab builds).
+static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int64_t nz, int64_t nz_total, int64_t x_per_launch = 0)
 {
     LinePlan P;
-    if (!hull_knob()) return P;
+    int mode = ctx->hull_mode < 0 ? hull_default() : ctx->hull_mode;
+    if (mode == HULL_AUTO) {
+        const int64_t lines = (x_per_launch > 0 ? x_per_launch : nx) * nz;
+        const bool narrow = (nz_total - 1) * (nz_total - 1) < (1 << 22);
+        mode = (lines >= (1 << 19) && ny >= 512 && ny <= 1024 && narrow) ? HULL_MIXED : HULL_BAND;
+    }
+    if (ny <= 1 && mode == HULL_MIXED) mode = HULL_BAND;        // no y pass
+    if (mode == HULL_BAND) return P;
     const int64_t N = nx * ny * nz;
     const int64_t hz = (nz_total - 1) * (nz_total - 1), hy = (ny - 1) * (ny - 1);
     P.wide_y = ny > 1024 || hz >= (1 << 22);
     P.wide_x = nx > 1024 || hz + hy >= (1 << 22);
-    P.polw_y = nx * ((ny + 31) / 32) * nz;
-    P.polw_x = ((nx + 31) / 32) * ny * nz;
-    const size_t stack_need = (size_t)N * ((P.wide_y || P.wide_x) ? 8 : 4);
-    const size_t pol_need = (size_t)(P.polw_y > P.polw_x ? P.polw_y : P.polw_x) * 4;
+    const int64_t polw_y = nx * ((ny + 31) / 32) * nz, polw_x = ((nx + 31) / 32) * ny * nz;
+    const bool wide = mode == HULL_LINE ? (P.wide_y || P.wide_x) : P.wide_y;
+    const int64_t polw = mode == HULL_LINE ? (polw_y > polw_x ? polw_y : polw_x) : polw_y;
     char keep[512]; memcpy(keep, ctx->err, sizeof(keep));
-    if (grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)N * 4) || grow(ctx, &ctx->d_stack, &ctx->stack_bytes, stack_need) ||
-        grow(ctx, &ctx->d_pol, &ctx->pol_bytes, pol_need)) {
+    if (grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)N * 4) || grow(ctx, &ctx->d_stack, &ctx->stack_bytes, (size_t)N * (wide ? 8 : 4)) ||
+        grow(ctx, &ctx->d_pol, &ctx->pol_bytes, (size_t)polw * 4)) {
         memcpy(ctx->err, keep, sizeof(keep));          // not an error: the in-place kernel needs no scratch
         return P;
     }
-    P.use = true;
+    P.mode = mode;
     return P;
 }
 
@@ -275,51 +288,49 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
         ctx->launches++;
     }
     const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz_total > 0 ? nz_total : nz);
+    int32_t* tmp = (int32_t*)ctx->d_tmp;
     CK(cudaEventRecord(ctx->ev[0], st), "event");
-    if (LP.use) {
-        // out of place: z pass -> A, y pass A -> B, x pass B -> A, with A = d_field unless there is no y pass
-        int32_t* tmp = (int32_t*)ctx->d_tmp;
-        int32_t* after_z = ny > 1 ? d_field : tmp;
-        CK(sdfb200::launch_binary_z(d_mask, after_z, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
-        ctx->launches++;
-        CK(cudaEventRecord(ctx->ev[1], st), "event");
-        // the y pass leaves its result with x and y swapped (tmp[y][x][z]): both passes then READ rows that are nz apart
-        // (input and stack of one line stay inside a few pages) and only their stores stride by a whole plane
-        if (ny > 1) {
-            CK(sdfb200::launch_line_hull(d_field, tmp, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz,
-                                         line_transposed() ? nx * nz : nz, line_transposed() ? nz : ny * nz, LP.wide_y, false,
-                                         res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
-            ctx->launches++;
-        }
-        CK(cudaEventRecord(ctx->ev[2], st), "event");
-        if (line_transposed())
-            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, nz, nz, ny, nx * nz, ny * nz, nz, LP.wide_x,
-                                         final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
-               "launch line_hull(x)");
-        else
-            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, ny * nz, ny * nz, 1, 0, ny * nz, 0, LP.wide_x,
-                                         final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
-               "launch line_hull(x)");
-        ctx->launches++;
-    } else {
-    CK(sdfb200::launch_binary_z(d_mask, d_field, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
+    // z pass: into the buffer the next pass reads
+    int32_t* after_z = d_field;
+    if (LP.mode == HULL_MIXED || (LP.mode == HULL_LINE && ny <= 1)) after_z = tmp;
+    CK(sdfb200::launch_binary_z(d_mask, after_z, (int)nz, nx * ny, d_carries, st, mask_bits), "launch binary_z");
     ctx->launches++;
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
-        CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, ctx->d_dbg, nullptr, 0, st),
-           "launch band_strided(y)");
+        if (LP.mode == HULL_LINE)            // field[x][y][z] -> tmp[y][x][z]
+            CK(sdfb200::launch_line_hull(d_field, tmp, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nx * nz, nz, LP.wide_y,
+                                         false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
+        else if (LP.mode == HULL_MIXED)      // tmp[x][y][z] -> field[x][y][z]
+            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nz, ny * nz, LP.wide_y,
+                                         false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
+        else
+            CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, ctx->d_dbg, nullptr, 0, st),
+               "launch band_strided(y)");
         ctx->launches++;
     }
     CK(cudaEventRecord(ctx->ev[2], st), "event");
-    CK(sdfb200::launch_band_strided(d_field, (int)nx, ny * nz, ny * nz, 1, 0, final_pass, res, ctx->d_ext, ctx->d_dbg ? ctx->d_dbg + 1024 * 8 : nullptr,
-                                    final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
-       "launch band_strided(x)");
+    if (LP.mode == HULL_LINE)                // tmp[y][x][z] -> field[x][y][z]
+        CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, nz, nz, ny, nx * nz, ny * nz, nz, LP.wide_x,
+                                     final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
+           "launch line_hull(x)");
+    else
+        CK(sdfb200::launch_band_strided(d_field, (int)nx, ny * nz, ny * nz, 1, 0, final_pass, res, ctx->d_ext,
+                                        ctx->d_dbg ? ctx->d_dbg + 1024 * 8 : nullptr, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
+           "launch band_strided(x)");
     ctx->launches++;
-    }
     CK(cudaEventRecord(ctx->ev[3], st), "event");
     ctx->timed = true;
     ctx->built = final_pass;
     ctx->res = res;
+    return SDF_B200_OK;
+}
+
+int sdf_b200_set_envelope_kernel(sdf_b200_ctx* ctx, int mode)
+{
+    if (!ctx) return SDF_B200_ERR_ARG;
+    if (mode < HULL_AUTO || mode > HULL_MIXED) return fail(ctx, SDF_B200_ERR_ARG, "envelope kernel: 0 auto, 1 band, 2 line, 3 mixed");
+    ctx->hull_mode = mode;
+    for (sdf_b200_ctx* p : ctx->peers) p->hull_mode = mode;
     return SDF_B200_OK;
 }
 
@@ -700,7 +711,7 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     uint8_t* d_mask = (uint8_t*)ctx->d_mask;
     int32_t* d_field = (int32_t*)ctx->d_out;
-    const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz);
+    const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz, (nx + NCH - 1) / NCH);
     int32_t* tmp = (int32_t*)ctx->d_tmp;
     const int64_t nwy = (ny + 31) / 32, nwx = (nx + 31) / 32;
     ctx->launches = 0;
@@ -732,32 +743,31 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
             CK(cudaEventRecord(ctx->chunk_ev[i], cs), "event");
             CK(cudaStreamWaitEvent(st, ctx->chunk_ev[i], 0), "wait");
         }
-        CK(sdfb200::launch_binary_z(d_mask + off, d_field + off, (int)nz, (x1 - x0) * ny, nullptr, st), "launch binary_z");
+        // (ny >= 64 here: there is always a y pass)
+        CK(sdfb200::launch_binary_z(d_mask + off, (LP.mode == HULL_MIXED ? tmp : d_field) + off, (int)nz, (x1 - x0) * ny, nullptr, st),
+           "launch binary_z");
         ctx->launches++;
-        if (ny > 1 && LP.use) {     // x-chunk of the y pass: reads field[x0..x1), writes tmp[y][x0..x1)[z]
-            CK(sdfb200::launch_line_hull(d_field + off, tmp + (line_transposed() ? x0 * nz : off), (char*)ctx->d_stack + (size_t)off * (LP.wide_y ? 8 : 4),
-                                         (uint32_t*)ctx->d_pol + x0 * nwy * nz, (int)ny, nz, nz, x1 - x0, plane,
-                                         line_transposed() ? nx * nz : nz, line_transposed() ? nz : plane, LP.wide_y, false, res, ctx->d_ext,
-                                         nullptr, 0, st), "launch line_hull(y)");
-            ctx->launches++;
-        } else if (ny > 1) {
+        char* stack_y = (char*)ctx->d_stack + (size_t)off * (LP.wide_y ? 8 : 4);
+        uint32_t* pol_y = (uint32_t*)ctx->d_pol + x0 * nwy * nz;
+        if (LP.mode == HULL_LINE)            // x-chunk of the y pass: field[x0..x1) -> tmp[y][x0..x1)[z]
+            CK(sdfb200::launch_line_hull(d_field + off, tmp + x0 * nz, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nx * nz, nz, LP.wide_y,
+                                         false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
+        else if (LP.mode == HULL_MIXED)      // tmp[x0..x1) -> field[x0..x1)
+            CK(sdfb200::launch_line_hull(tmp + off, d_field + off, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nz, plane, LP.wide_y,
+                                         false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
+        else
             CK(sdfb200::launch_band_strided(d_field + off, (int)ny, nz, nz, x1 - x0, plane, false, res, ctx->d_ext, nullptr,
                                             nullptr, 0, st), "launch band_strided(y)");
-            ctx->launches++;
-        }
+        ctx->launches++;
     }
     for (int j = 0; j < NCH; ++j) {                                 // ---- final x pass + download, chunked along y
         const int64_t y0 = ny * j / NCH, y1 = ny * (j + 1) / NCH;
         if (y1 == y0) continue;
         const int64_t col0 = y0 * nz, ncols = (y1 - y0) * nz;
-        if (LP.use && line_transposed())      // y-chunk of the x pass: reads tmp[y0..y1), writes field[.][y0..y1)[z]
+        if (LP.mode == HULL_LINE)            // y-chunk of the x pass: tmp[y0..y1) -> field[.][y0..y1)[z]
             CK(sdfb200::launch_line_hull(tmp + y0 * nx * nz, d_field + col0, (char*)ctx->d_stack + (size_t)(y0 * nx * nz) * (LP.wide_x ? 8 : 4),
                                          (uint32_t*)ctx->d_pol + y0 * nwx * nz, (int)nx, nz, nz, y1 - y0, nx * nz, plane, nz, LP.wide_x, true,
                                          res, ctx->d_ext, ctx->d_lut, LUT_N, st), "launch line_hull(x)");
-        else if (LP.use)
-            CK(sdfb200::launch_line_hull(tmp + col0, d_field + col0, (char*)ctx->d_stack + (size_t)col0 * (LP.wide_x ? 8 : 4), (uint32_t*)ctx->d_pol + col0 * nwx,
-                                         (int)nx, plane, ncols, 1, 0, plane, 0, LP.wide_x, true, res, ctx->d_ext, ctx->d_lut, LUT_N, st),
-               "launch line_hull(x)");
         else
             CK(sdfb200::launch_band_strided(d_field + col0, (int)nx, plane, ncols, 1, 0, true, res, ctx->d_ext, nullptr,
                                             ctx->d_lut, LUT_N, st), "launch band_strided(x)");

@@ -54,9 +54,7 @@ template <> struct LineEntry<false> {
     static constexpr uint32_t TERM = 0xffffffffu;
     static SDF_HD type pack(int pos, int32_t h) { return ((uint32_t)pos << 22) | (uint32_t)h; }
     static SDF_HD bool is_term(type e) { return e == TERM; }
-    static SDF_HD bool is_special(type e) { return e >= 0xfffffffeu; }     // terminator or "not copied yet" marker
     static SDF_HD type term() { return TERM; }
-    static SDF_HD type empty() { return 0xfffffffeu; }
     static SDF_HD int pos(type e) { return (int)(e >> 22); }
     static SDF_HD int32_t h(type e) { return (int32_t)(e & 0x3fffffu); }
 };
@@ -64,9 +62,7 @@ template <> struct LineEntry<true> {
     typedef unsigned long long type;
     static SDF_HD type pack(int pos, int32_t h) { return ((unsigned long long)(uint32_t)pos << 32) | (uint32_t)h; }
     static SDF_HD bool is_term(type e) { return (e >> 32) == 0xffffffffull; }
-    static SDF_HD bool is_special(type e) { return (e >> 32) >= 0xfffffffeull; }
     static SDF_HD type term() { return 0xffffffff00000000ull; }
-    static SDF_HD type empty() { return 0xfffffffe00000000ull; }
     static SDF_HD int pos(type e) { return (int)(e >> 32); }
     static SDF_HD int32_t h(type e) { return (int32_t)(e & 0xffffffffull); }
 };
@@ -86,82 +82,61 @@ SDF_HD bool lh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t
 #define LH_CTZ(x) __builtin_ctz(x)
 #endif
 
-// Per-thread scratch of one line pass: 8 entry slots (a ring indexed modulo 8), private to the thread.
-//   build sweep : a write-through copy of the top of the stack (slot = depth index), so pops read shared memory;
-//   query sweep : a FIFO of hull entries copied ahead of the walk with asynchronous global->shared copies.
-// The host stand-in applies asynchronous copies only at wait(), so a read that does not wait for its copy fails tests.
-template <bool WIDE> struct HostLineMem {
-    typedef typename LineEntry<WIDE>::type ent_t;
-    ent_t slot[8]; ent_t pend_val[8]; int pend_k[8]; int npend = 0;
-    void ring_st(int k, ent_t e) { slot[k & 7] = e; }
-    ent_t ring_ld(int k) const { return slot[k & 7]; }
-    void fifo_issue(int k, const ent_t* src) { pend_k[npend] = k & 7; pend_val[npend] = *src; ++npend; }
-    void fifo_commit() {}
-    void fifo_landed_hint() { fifo_wait(); }          // host only: copies issued a block ago have landed by now
-    void fifo_wait() { for (int i = 0; i < npend; ++i) slot[pend_k[i]] = pend_val[i]; npend = 0; }
-    ent_t fifo_ld(int k) const { return slot[k & 7]; }
-};
-
 // One line.  in / stk: element 0 of the line, consecutive positions `stride` elements apart (stk in entries);
-// pol: word 0 of the line's polarity bits, consecutive words `pstride` elements apart.  emit(k, m, neg) receives the
-// squared distance m (<= SDF_INF) and the polarity of positions 0, 1, .. n-1 in order, k = position modulo 8;
-// flush(cnt) follows every 8 positions (cnt = 8) and the last cnt < 8 of the line: the caller may batch its stores there.
+// pol: word 0 of the line's polarity bits, consecutive words `pstride` elements apart.  emit(m, neg) receives the
+// squared distance m (<= SDF_INF) and the polarity of positions 0, 1, .. n-1 in order.
 //
 // Chain of a run [a,e), bottom to top:  B, v0, v1, ..  with B the left boundary site (a-1, 0) -- for a = 0 the site
 // (-1, 2^30), which can never win and so stands for "nothing on the left".  Only the vertices v_i are stored (slot a+i).
-// The build keeps the top three elements in registers (T, S unpacked; R = v_{d-3} as a packed entry) and the top eight
-// also in the thread's ring, so a pop normally costs one shared-memory read that is not needed before the next pop.
-template <bool WIDE, typename Mem, typename Emit, typename Flush>
+// The build keeps the top three elements in registers (T, S unpacked; R = v_{d-3} as a packed entry): a pop refills R
+// with a load whose result is not needed before the next pop.  The query sweep likewise holds the entry after `next`
+// in a register, fetched one advance ahead.
+//
+// (Variants that were measured and dropped, see DESIGN.md: a shared-memory ring for the top of the stack, write-back
+// instead of write-through pushes, an asynchronous-copy FIFO for the query sweep.  Each removed stalls or L2 traffic
+// but cost more issue slots than it saved; this kernel is issue-bound.)
+template <bool WIDE, typename Emit>
 SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n, typename LineEntry<WIDE>::type* __restrict__ stk,
-                           uint32_t* __restrict__ pol, int64_t pstride, Mem& mem, Emit emit, Flush flush)
+                           uint32_t* __restrict__ pol, int64_t pstride, Emit emit)
 {
     typedef LineEntry<WIDE> E;
     typedef typename E::type ent_t;
     constexpr int32_t BIG = 0x40000000;              // height of the "nothing on the left" boundary site
     constexpr int32_t NOSITE = 0x60000000;           // height of a non-existent next point: never wins
-    constexpr int K = 8;                             // ring slots
     if (n <= 0) return;
     // ------------------------------------------------------------------------------------------------ build sweep
     {
-        // Write-back ring: the vertices v_i, lo <= i < d, exist ONLY in the thread's ring (slot i modulo 8); those below
-        // lo are in the global stack.  A push into a full ring first moves v_lo out to global memory; a vertex popped
-        // while still in the ring never costs a global store.  The ring is written out when its run ends.
-        int a = 0, d = 0, lo = 0;                    // current run start; vertices on its stack; first ring-resident one
+        int a = 0, d = 0;                            // current run start; number of vertices on its stack
         int bpos = -1; int32_t bY = 1 + BIG;         // left boundary site of the run (lifted height)
         int tp = bpos; int32_t tY = bY;              // T: top of the chain
         int sp = tp; int32_t sY = tY + 1;            // S: below T, or the none-sentinel (sp == tp: the hull test is false)
         ent_t R = 0;                                 // v_{d-3} when it exists
-        ent_t* lop = stk;                            // global slot a + lo
+        ent_t* top = stk;                            // slot a + d
+        const int64_t stride3 = 3 * stride;
         bool prevpol = in[0] < 0;
         auto pop_against = [&](int qp, int32_t qY) {
             while (lh_dominated(sp, sY, tp, tY, qp, qY)) {
                 LH_TICK(2);
                 --d;
-                if (d < lo) { lo = d; lop -= stride; }                       // the popped vertex was already in global memory
+                top -= stride;
                 tp = sp; tY = sY;
                 if (d >= 2) {
                     sp = E::pos(R); sY = sp * sp + E::h(R);                  // v_{d-2}
-                    if (d - 3 >= lo) R = mem.ring_ld(d - 3);                 // v_{d-3}
-                    else if (d >= 3) { LH_TICK(5); R = *(lop - (int64_t)(lo - (d - 3)) * stride); }
+                    if (d >= 3) R = *(top - stride3);                        // v_{d-3}
                 } else if (d == 1) { sp = bpos; sY = bY; }
                 else { sp = tp; sY = tY + 1; }                               // T is the boundary site: nothing below
             }
-        };
-        auto write_out = [&](int e) {                // the run [a, e) is complete: ring -> global, then the terminator
-            ent_t* q = lop;
-            for (int i = lo; i < d; ++i) { *q = mem.ring_ld(i); q += stride; }
-            if (d < e - a) *q = E::term();
         };
         auto row = [&](int y, int32_t v, bool p) {
             LH_TICK(0);
             if (p != prevpol) {                      // a run ends at y-1 and the next starts at y
                 LH_TICK(3);
                 pop_against(y, y * y);               // close against the right boundary site (y, 0)
-                write_out(y);
-                a = y; d = 0; lo = 0;
+                if (d < y - a) *top = E::term();
+                a = y; d = 0;
                 bpos = y - 1; bY = bpos * bpos;
                 tp = bpos; tY = bY; sp = tp; sY = tY + 1;
-                lop = stk + (int64_t)y * stride;
+                top = stk + (int64_t)y * stride;
                 prevpol = p;
             }
             const int32_t h = p ? -v : v;
@@ -169,106 +144,99 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 LH_TICK(1);
                 const int32_t Y = y * y + h;
                 pop_against(y, Y);
-                if (d - lo == K) { *lop = mem.ring_ld(lo); lop += stride; ++lo; }    // ring full: its oldest vertex moves out
-                mem.ring_st(d, E::pack(y, h));
+                *top = E::pack(y, h);
+                top += stride;
                 ++d;
                 R = E::pack(sp, sY - sp * sp);       // (garbage when S is not a vertex: then never used)
                 sp = tp; sY = tY;
                 tp = y; tY = Y;
             }
         };
-        // one row per iteration (a single copy of the row code keeps the kernel inside the instruction cache); the
-        // next row's value is requested a whole row of work ahead
+        constexpr int U = 4;                         // rows read ahead of the (data-dependent) stack work
         const int32_t* ip = in;
         uint32_t* pp = pol;
         uint32_t pw = 0;
-        int32_t vnext = LH_LDCS(ip); ip += stride;
-        for (int y = 0; y < n; ++y) {
-            const int32_t v = vnext;
-            if (y + 1 < n) { vnext = LH_LDCS(ip); ip += stride; }
-            const bool p = v < 0;
-            row(y, v, p);
-            pw |= (uint32_t)p << (y & 31);
-            if ((y & 31) == 31 || y == n - 1) { *pp = pw; pp += pstride; pw = 0; }
+        int32_t vnx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { vnx[u] = (u < n) ? LH_LDCS(ip) : 0; ip += stride; }
+        int y0 = 0;
+        for (; y0 + 2 * U <= n; y0 += U) {           // whole groups with a whole group to read ahead: no bounds checks
+            int32_t vin[U];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vin[u] = vnx[u]; bits |= ((uint32_t)vin[u] >> 31) << u; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vnx[u] = LH_LDCS(ip); ip += stride; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) row(y0 + u, vin[u], (bits >> u) & 1u);
+            pw |= bits << (y0 & 31);
+            if ((y0 & 31) == 32 - U) { *pp = pw; pp += pstride; pw = 0; }
         }
-        write_out(n);                                // the last run has no right boundary site
+        for (; y0 < n; y0 += U) {                    // the last one or two groups
+            int32_t vin[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) vin[u] = vnx[u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vnx[u] = (y0 + U + u < n) ? LH_LDCS(ip) : 0; ip += stride; }
+            for (int u = 0; u < U && y0 + u < n; ++u) {
+                const bool p = vin[u] < 0;
+                row(y0 + u, vin[u], p);
+                pw |= (uint32_t)p << ((y0 + u) & 31);
+            }
+            if ((y0 & 31) == 32 - U || y0 + U >= n) { *pp = pw; pp += pstride; pw = 0; }
+        }
+        if (d < n - a) *top = E::term();             // the last run has no right boundary site
     }
     // ------------------------------------------------------------------------------------------------ query sweep
     {
         int e = 0;                                   // end of the current run (the first run starts at 0)
         int cpos = 0, npos = 0;                      // current / next point of the run's hull (vertex or boundary site)
         int32_t ch = BIG, nh = NOSITE;
-        // FIFO of the run's stack entries in the ring: fi copies issued, ci consumed (slot = count modulo 8); cnt = slots
-        // the run owns (e - a); gp = address of the next slot to copy.  A consumed slot is overwritten with the "empty"
-        // marker, so a read that runs ahead of its copy sees the marker and takes the slow path: no landing bookkeeping.
-        int fi = 0, ci = 0, cnt = 0;
-        const ent_t* gp = stk;
-        bool tail = true, neg = false, ended = true; // ended: the terminator was consumed (nothing more to copy)
-        auto top_up = [&]() {                        // copy ahead until the FIFO is full or the run's slots are exhausted
-            mem.fifo_landed_hint();
-            int want = K - (fi - ci);
-            want = want < cnt - fi ? want : cnt - fi;
-            if (ended) want = 0;
-            for (; want > 0; --want) { mem.fifo_issue(fi, gp); gp += stride; ++fi; }
-            mem.fifo_commit();
-        };
-        // the rare cases of advance(): entry not copied yet, terminator, run exhausted, or already past the last point
-        auto advance_slow = [&](ent_t en) {
-            nh = NOSITE;
-            if (tail) return;
-            if (!E::is_term(en) && ci < cnt) {       // starved: burst of advances, or the run just started
-                LH_TICK(6);
-                if (fi == ci) top_up();
-                mem.fifo_wait();
-                en = mem.fifo_ld(ci);
-                if (!E::is_term(en)) { mem.ring_st(ci, E::empty()); ++ci; npos = E::pos(en); nh = E::h(en); return; }
-            }
-            ended = true; tail = true; npos = e; nh = (e < n) ? 0 : NOSITE;
-        };
-        // next <- the point after it: the following stack entry, then the right boundary site (e, 0), then nothing
+        ent_t NE = E::term();                        // the stack entry after `next`, fetched ahead (terminator: none)
+        const ent_t* fp = stk;                       // slot after NE's
+        int left = 0;                                // slots of the run not fetched yet
+        bool tail = true, neg = false;
+        // next <- the point after it: the entry fetched ahead, then the right boundary site (e, 0), then nothing
         auto advance = [&]() {
             cpos = npos; ch = nh;
-            const ent_t en = mem.fifo_ld(ci);
-            if (!E::is_special(en)) { mem.ring_st(ci, E::empty()); ++ci; npos = E::pos(en); nh = E::h(en); }
-            else advance_slow(en);
+            if (!E::is_term(NE)) {
+                npos = E::pos(NE); nh = E::h(NE);
+                NE = E::term();
+                if (left > 0) { NE = *fp; fp += stride; --left; }
+            } else if (!tail) { tail = true; npos = e; nh = (e < n) ? 0 : NOSITE; }
+            else nh = NOSITE;
         };
         const uint32_t* pp = pol;
         const int nw = (n + 31) >> 5;
         for (int w = 0; w < nw; ++w) {
             const uint32_t pw = *pp; pp += pstride;
             const int yend = (w + 1) * 32 < n ? (w + 1) * 32 : n;
-            for (int yb = w * 32; yb < yend; yb += K) {
-                top_up();                            // block of 8 positions: refill what the previous block consumed
-                const int ye = yb + K < yend ? yb + K : yend;
-                for (int y = yb; y < ye; ++y) {
-                    if (y == e) {                    // a run starts here: find its end, restart the walk
-                        neg = (pw >> (y & 31)) & 1u;
-                        uint32_t x = (neg ? ~pw : pw) & ~((2u << (y & 31)) - 1u);      // later positions of the other polarity
-                        int w2 = w;
-                        const uint32_t* p2 = pp;
-                        while (!x && ++w2 < nw) { const uint32_t q = *p2; p2 += pstride; x = neg ? ~q : q; }
-                        e = x ? (w2 << 5) + LH_CTZ(x) : n;
-                        if (e > n) e = n;            // (the bits past the end of the line are zero)
-                        mem.fifo_wait();             // copies of the previous run still in flight must not land later
-#pragma unroll
-                        for (int k = 0; k < K; ++k) mem.ring_st(k, E::empty());
-                        gp = stk + (int64_t)y * stride;
-                        cnt = e - y; fi = 0; ci = 0; ended = false; tail = false;
-                        npos = y - 1; nh = y > 0 ? 0 : BIG;   // the left boundary site becomes `current` ...
-                        advance();                   // ... and the first vertex (or the right boundary site) `next`
-                    }
-                    for (;;) {
-                        const int dc = y - cpos, dn = y - npos;
-                        const int32_t vc = dc * dc + ch, vn = dn * dn + nh;
-                        if (vn > vc) {
-                            emit(y - yb, vc < SDF_INF ? vc : (int32_t)SDF_INF, neg);
-                            break;
-                        }
-                        LH_TICK(4);
-                        advance();
-                    }
+            for (int y = w * 32; y < yend; ++y) {
+                if (y == e) {                        // a run starts here: find its end, restart the walk
+                    neg = (pw >> (y & 31)) & 1u;
+                    uint32_t x = (neg ? ~pw : pw) & ~((2u << (y & 31)) - 1u);  // later positions of the other polarity
+                    int w2 = w;
+                    const uint32_t* p2 = pp;
+                    while (!x && ++w2 < nw) { const uint32_t q = *p2; p2 += pstride; x = neg ? ~q : q; }
+                    e = x ? (w2 << 5) + LH_CTZ(x) : n;
+                    if (e > n) e = n;                // (the bits past the end of the line are zero)
+                    fp = stk + (int64_t)y * stride;
+                    left = e - y;
+                    NE = *fp; fp += stride; --left;  // (left >= 1 here)
+                    tail = false;
+                    npos = y - 1; nh = y > 0 ? 0 : BIG;       // the left boundary site becomes `current` ...
+                    advance();                       // ... and the first vertex (or the right boundary site) `next`
                 }
-                flush(ye - yb);
+                for (;;) {
+                    const int dc = y - cpos, dn = y - npos;
+                    const int32_t vc = dc * dc + ch, vn = dn * dn + nh;
+                    if (vn > vc) {
+                        emit(vc < SDF_INF ? vc : (int32_t)SDF_INF, neg);
+                        break;
+                    }
+                    LH_TICK(4);
+                    advance();
+                }
             }
         }
     }

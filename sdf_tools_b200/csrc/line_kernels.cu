@@ -12,34 +12,13 @@
 
 namespace sdfb200 {
 
-// The thread's eight ring slots in shared memory: slot k of thread t at ring[k * TPB + t] (conflict-free).
-template <bool WIDE, int TPB> struct DevLineMem {
-    typedef typename LineEntry<WIDE>::type ent_t;
-    ent_t* ring;                                     // &ring[threadIdx.x]
-    __device__ __forceinline__ void ring_st(int k, ent_t e) { ring[(k & 7) * TPB] = e; }
-    __device__ __forceinline__ ent_t ring_ld(int k) const { return ring[(k & 7) * TPB]; }
-    __device__ __forceinline__ void fifo_issue(int k, const ent_t* src)
-    {
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (k & 7) * TPB);
-        if (WIDE) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
-        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
-    }
-    __device__ __forceinline__ void fifo_landed_hint() {}
-    __device__ __forceinline__ void fifo_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-    __device__ __forceinline__ void fifo_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-    __device__ __forceinline__ ent_t fifo_ld(int k) const { return ring[(k & 7) * TPB]; }
-};
-
 template <bool WIDE, bool FINAL, int TPB>
-__global__ void __launch_bounds__(TPB, 1024 / TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+__global__ void __launch_bounds__(TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
                                                         typename LineEntry<WIDE>::type* __restrict__ stk, uint32_t* __restrict__ pol,
                                                         int n, int64_t line_stride, int64_t ncols, int64_t nlines, int64_t outer_stride,
                                                         int64_t out_stride, int64_t out_outer_stride,
                                                         double res, int* __restrict__ ext, const float* __restrict__ lut, int lut_n)
 {
-    typedef typename LineEntry<WIDE>::type ent_t;
-    __shared__ ent_t ring[8 * TPB];
-    __shared__ int32_t blk[FINAL ? 8 * TPB : 1];      // final pass: the 8 results of a block, converted and stored together
     const int64_t lid = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const bool ok = lid < nlines;
     int32_t maxpos = 0, maxneg = 0;
@@ -48,37 +27,25 @@ __global__ void __launch_bounds__(TPB, 1024 / TPB) line_hull_kernel(const int32_
         const int64_t base = outer * outer_stride + col;
         const int nw = (n + 31) >> 5;
         int32_t* dst = out + outer * out_outer_stride + col;
-        DevLineMem<WIDE, TPB> mem{ring + threadIdx.x};
-        int32_t* myblk = blk + (FINAL ? threadIdx.x : 0);
-        auto to_float = [&](int32_t v) -> float {     // (float)(sqrt((double)d2) * res) with the polarity sign (sdf_generation.hpp:254-265)
-            const int32_t m = v < 0 ? -v : v;
-            float f;
-            if (m < lut_n) f = __ldg(lut + m);
-            else f = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
-            return v < 0 ? -f : f;
-        };
-        line_hull_pass<WIDE>(in + base, line_stride, n, stk + base, pol + outer * (int64_t)nw * ncols + col, ncols, mem,
-            [&](int k, int32_t m, bool neg) {
+        // final pass: the table load of one position is issued a whole position before its result is stored
+        float fpend = 0.f;
+        bool negpend = false, first = true;
+        line_hull_pass<WIDE>(in + base, line_stride, n, stk + base, pol + outer * (int64_t)nw * ncols + col, ncols,
+            [&](int32_t m, bool neg) {
                 if (FINAL) {
                     if (neg) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);
-                    myblk[k * TPB] = neg ? -m : m;
+                    if (!first) { __stcs(reinterpret_cast<float*>(dst), negpend ? -fpend : fpend); dst += out_stride; }
+                    first = false;
+                    // (float)(sqrt((double)d2) * res), the value the combine loop stores (sdf_generation.hpp:254-265)
+                    if (m < lut_n) fpend = __ldg(lut + m);
+                    else fpend = (m >= SDF_INF) ? __int_as_float(0x7f800000) : (float)(sqrt((double)m) * res);
+                    negpend = neg;
                 } else {
                     __stcs(dst, neg ? -m : m);
                     dst += out_stride;
                 }
-            },
-            [&](int cnt) {
-                if (!FINAL) return;
-                if (cnt == 8) {                      // eight independent table loads in flight, then eight stores
-                    float f[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) f[k] = to_float(myblk[k * TPB]);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) { __stcs(reinterpret_cast<float*>(dst), f[k]); dst += out_stride; }
-                } else {
-                    for (int k = 0; k < cnt; ++k) { __stcs(reinterpret_cast<float*>(dst), to_float(myblk[k * TPB])); dst += out_stride; }
-                }
             });
+        if (FINAL && !first) __stcs(reinterpret_cast<float*>(dst), negpend ? -fpend : fpend);
     }
     if (FINAL) {
         maxpos = __reduce_max_sync(0xffffffffu, maxpos);

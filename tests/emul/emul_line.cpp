@@ -16,11 +16,8 @@ static void pass_lines(const int32_t* in, int32_t* out, int n, int64_t line_stri
     for (int64_t c = 0; c < ncols; c++)
     {
         int32_t* dst = out + c;
-        HostLineMem<WIDE> mem;
-        int32_t blk[8];
-        line_hull_pass<WIDE>(in + c, line_stride, n, stk.data() + c, pol.data() + c, ncols, mem,
-                             [&](int k, int32_t m, bool neg) { blk[k] = neg ? -m : m; },
-                             [&](int cnt) { for (int k = 0; k < cnt; ++k) { *dst = blk[k]; dst += line_stride; } });
+        line_hull_pass<WIDE>(in + c, line_stride, n, stk.data() + c, pol.data() + c, ncols,
+                             [&](int32_t m, bool neg) { *dst = neg ? -m : m; dst += line_stride; });
     }
 }
 

@@ -274,3 +274,49 @@ def test_axis_limit_is_documented(ctx):
     with pytest.raises(SdfB200Error) as e:                        # 3 slabs of 1024 planes = 3072 > 2048
         ctx.slab_build_device(m.data_ptr(), 2, 2, 1024, 1.0, s.data_ptr(), [1024, 1024, 1024], 1, o.data_ptr())
     assert e.value.code == _capi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("mode", ["band", "line", "mixed"])
+def test_envelope_kernel_modes(ctx, mode):
+    """sdf_b200_set_envelope_kernel: the banded in-place kernel, the line-per-thread kernel (hull stacks in a device
+    scratch; 64-bit stack entries when a line is longer than 1024 or heights can reach 2^22) and their mix must all
+    reproduce the oracle bit for bit -- random, structured, thin, ragged (sizes that are not multiples of 32 or of the
+    warp) and long-axis grids, single-polarity lines, the slab path and the chunked host path."""
+    from sdf_tools_b200.distributed import slab_ranges
+    ctx.set_envelope_kernel(mode)
+    try:
+        for shape, p, seed in [((64, 64, 64), 0.30, 1), ((33, 47, 29), 0.05, 2), ((1, 40, 20), 0.1, 3), ((40, 1, 20), 0.1, 4),
+                               ((20, 40, 1), 0.1, 5), ((7, 5, 3), 0.5, 6), ((96, 128, 160), 0.002, 8), ((130, 70, 257), 0.3, 9),
+                               ((2, 2, 2), 0.5, 10), ((1, 1, 1), 1.0, 11), ((300, 31, 65), 0.9, 12), ((50, 60, 70), 0.0, 13),
+                               ((50, 60, 70), 1.0, 14)]:
+            check_full(ctx, synth.iid(shape, p, seed), 0.1)
+        for shape in [(2048, 4, 8), (4, 2048, 8), (4, 8, 2048), (1500, 3, 33), (1100, 1030, 5)]:     # wide stack entries
+            check_full(ctx, synth.iid(shape, 0.003, 21), 0.01)
+        check_full(ctx, synth.make_mask("c3", (160, 192, 128)), 0.01)
+        check_full(ctx, synth.make_mask("c5", (128, 128, 128)), 0.02)
+        check_full(ctx, synth.make_mask("c2", (96, 96, 96)), 0.01)
+        # slab protocol on one device (z-distances reach across slabs: heights of the y / x passes see the whole axis)
+        mask = synth.make_mask("c3", (96, 80, 128))
+        nx, ny, nz = mask.shape
+        want, (wmx, wmn) = ctx.build_from_mask(mask, 0.05)
+        ranges = slab_ranges(nz, 4)
+        widths = [b - a for a, b in ranges]
+        slabs = [torch.from_numpy(np.ascontiguousarray(mask[:, :, a:b])).cuda() for a, b in ranges]
+        allsum = torch.empty(4 * nx * ny, dtype=torch.int32, device="cuda")
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for r, s in enumerate(slabs):
+            ctx.slab_summary_device(s.data_ptr(), nx, ny, widths[r], allsum[r * nx * ny:].data_ptr())
+        outs = []
+        for r, s in enumerate(slabs):
+            o = torch.empty((nx, ny, widths[r]), dtype=torch.float32, device="cuda")
+            ctx.slab_build_device(s.data_ptr(), nx, ny, widths[r], 0.05, allsum.data_ptr(), widths, r, o.data_ptr(), keep_extrema=(r > 0))
+            outs.append(o.cpu().numpy())
+        assert np.array_equal(np.concatenate(outs, axis=2).view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(want.view(np.uint32), O.build_sdf(mask, 0.05)[0].view(np.uint32))
+        # chunked host path (>= 2^25 voxels)
+        big = synth.iid((300, 264, 430), 0.02, 17)
+        want, wmx, wmn = O.build_sdf(big, 0.05)
+        got, (mx, mn) = ctx.build_from_mask(big, 0.05)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and (mx, mn) == (wmx, wmn)
+    finally:
+        ctx.set_envelope_kernel("auto")
