@@ -45,7 +45,7 @@ PASS_KERNEL = {"pass1_z_ms": "binary_z_kernel", "pass2_y_ms": "band_strided_kern
 def kernel_source_hash() -> str:
     """sha256 over the CUDA sources of the build kernels: ties an ncu capture to the code it was taken from."""
     h = hashlib.sha256()
-    for f in ("edt_kernels.cu", "band_hull.cuh"):
+    for f in ("edt_kernels.cu", "band_hull.cuh", "line_kernels.cu", "line_hull.cuh"):
         with open(os.path.join(ROOT, "sdf_tools_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -377,7 +377,11 @@ def main():
     dom = max(means, key=lambda k: means[k])
     dom_gbs = PASS_BYTES[dom] * nvox / (means[dom] * 1e-3) / 1e9
     whole_gbs = ALGO_BYTES_PER_VOXEL * nvox / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": PASS_KERNEL[dom],
+    env_kernel = ctx.last_envelope_kernel()
+    pass_kernel = dict(PASS_KERNEL)
+    if env_kernel in ("line", "mixed"): pass_kernel["pass2_y_ms"] = "line_hull_kernel (y)"
+    if env_kernel == "line": pass_kernel["pass3_x_ms"] = "line_hull_kernel (x, final)"
+    roofline = {"bound": "hbm", "kernel": pass_kernel[dom], "envelope_kernels": env_kernel,
                 "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
                 "traffic": ncu_traffic(dom, nvox), "algorithmic_bytes_per_launch": PASS_BYTES[dom] * nvox,
                 "peak_source": peak_src, "algorithmic_bytes_per_voxel": PASS_BYTES[dom],

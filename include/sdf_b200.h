@@ -192,6 +192,8 @@ int sdf_b200_gradient_host(sdf_b200_ctx* ctx, const float* sdf, int64_t nx, int6
 int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4);
 /* Number of kernels the last build launched (for bench.py's gpu_launches). */
 int sdf_b200_last_launches(const sdf_b200_ctx* ctx);
+/* Envelope kernels the last build on this context used: 1 band, 2 line, 3 mixed (sdf_b200_set_envelope_kernel). */
+int sdf_b200_last_envelope_kernel(const sdf_b200_ctx* ctx);
 
 /* Diagnostics: when enabled, thread 0 of the first 1024 CTAs of each envelope pass stores clock64() at its phase
  * boundaries (start, loaded, built, barrier, merged, queried) into a device buffer; `out` (2*1024*8 values, pass 2

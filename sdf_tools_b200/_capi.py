@@ -46,6 +46,7 @@ SYMBOLS = [
     ("sdf_b200_gradient_host", _int, [_vp, _vp, _i64, _i64, _i64, _dbl, _int, _int, _vp]),
     ("sdf_b200_last_timing", _int, [_vp, C.POINTER(C.c_float)]),
     ("sdf_b200_last_launches", _int, [_vp]),
+    ("sdf_b200_last_envelope_kernel", _int, [_vp]),
     ("sdf_b200_debug_phase_clocks", _int, [_vp, _int, C.POINTER(C.c_longlong), _int]),
 ]
 

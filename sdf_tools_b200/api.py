@@ -230,6 +230,10 @@ class Context:
     def last_launches(self) -> int:
         return int(self._lib.sdf_b200_last_launches(self._h))
 
+    def last_envelope_kernel(self) -> str:
+        """Envelope kernels the last build used: "band", "line" or "mixed"."""
+        return {1: "band", 2: "line", 3: "mixed"}.get(int(self._lib.sdf_b200_last_envelope_kernel(self._h)), "band")
+
 
 def build_sdf(mask: np.ndarray, resolution: float, device: int = 0):
     """One-shot helper: (sdf, (max, min)) for a host mask."""

@@ -35,6 +35,7 @@ struct sdf_b200_ctx {
     void* d_grad = nullptr; size_t grad_bytes = 0;  // gradient staging of the host entry point
     void* d_out2 = nullptr; size_t out2_bytes = 0;  // second result buffer of the batched object builds
     int* d_ext_objs = nullptr; size_t ext_objs_n = 0;
+    int last_hull = 1;                              // envelope kernels the last build resolved to (HULL_BAND / LINE / MIXED)
     int hull_mode = -1;                             // -1: SDF_B200_HULL default; else HULL_AUTO / BAND / LINE / MIXED (sdf_b200_set_envelope_kernel)
     // scratch of the line-per-thread envelope passes: the field between the y and x passes, the hull stacks, polarity bits
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
@@ -288,6 +289,7 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
         ctx->launches++;
     }
     const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz_total > 0 ? nz_total : nz);
+    ctx->last_hull = LP.mode;
     int32_t* tmp = (int32_t*)ctx->d_tmp;
     CK(cudaEventRecord(ctx->ev[0], st), "event");
     // z pass: into the buffer the next pass reads
@@ -712,6 +714,7 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
     uint8_t* d_mask = (uint8_t*)ctx->d_mask;
     int32_t* d_field = (int32_t*)ctx->d_out;
     const LinePlan LP = plan_line_passes(ctx, nx, ny, nz, nz, (nx + NCH - 1) / NCH);
+    ctx->last_hull = LP.mode;
     int32_t* tmp = (int32_t*)ctx->d_tmp;
     const int64_t nwy = (ny + 31) / 32, nwx = (nx + 31) / 32;
     ctx->launches = 0;
@@ -823,6 +826,7 @@ int sdf_b200_last_timing(sdf_b200_ctx* ctx, float* out_ms4)
 }
 
 int sdf_b200_last_launches(const sdf_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sdf_b200_last_envelope_kernel(const sdf_b200_ctx* ctx) { return ctx ? ctx->last_hull : 0; }
 
 int sdf_b200_debug_phase_clocks(sdf_b200_ctx* ctx, int enable, long long* out, int n)
 {

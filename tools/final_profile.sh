@@ -8,7 +8,7 @@ timeout 300 python bench.py --impl reference > gpurun_out/${R}_bench_reference.j
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-c4 --no-same-config > gpurun_out/b_ncu.log 2>&1
 timeout 300 tools/ncu_counts.sh
 cp gpurun_out/counts_libsdf_b200.csv gpurun_out/${R}_counters.csv
-timeout 400 ncu --set full --clock-control none --import-source on --kernel-name regex:'binary_z|band_strided' -s 3 -c 3 -o gpurun_out/${R}_prof -f python tools/one_build.py c3 > gpurun_out/${R}_ncu_full.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on --kernel-name regex:'binary_z|band_strided|line_hull' -s 3 -c 3 -o gpurun_out/${R}_prof -f python tools/one_build.py c3 > gpurun_out/${R}_ncu_full.log 2>&1
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${R}_gpu.csv
 lscpu | head -20 > gpurun_out/${R}_lscpu.txt
 python - <<P

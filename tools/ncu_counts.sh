@@ -7,5 +7,5 @@ python tools/one_build.py c3 > /dev/null 2>&1   # caches the mask
 if [ -d sdf_tools_b200/lib/variants ]; then LIBS=$(ls sdf_tools_b200/lib/variants/*.so); else LIBS=sdf_tools_b200/lib/libsdf_b200.so; fi
 for lib in $LIBS; do
   n=$(basename $lib .so)
-  SDF_B200_LIB=$PWD/$lib timeout 300 ncu --metrics $M --clock-control none --kernel-name regex:'binary_z|band_strided' -c 3 --csv --log-file gpurun_out/counts_$n.csv python tools/one_build.py c3 > /dev/null 2>&1
+  SDF_B200_LIB=$PWD/$lib timeout 300 ncu --metrics $M --clock-control none --kernel-name regex:'binary_z|band_strided|line_hull' -c 3 --csv --log-file gpurun_out/counts_$n.csv python tools/one_build.py c3 > /dev/null 2>&1
 done

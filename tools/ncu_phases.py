@@ -35,3 +35,20 @@ for k in kernels:
             print(f"| SASS [{prev}, {bi}] {k['rows'][bi][ia].strip().split()[0]} | {si / 1e6:.0f} M | {100 * si / tot:.1f} % | {st / si:.1f} | {100 * ss / tots:.1f} % |")
         prev = bi + 1
     print()
+
+# line-per-thread kernel: no barriers to cut at -- totals and the SASS lines where warps wait the most
+seen = set()
+for k in kernels:
+    if "line_hull" not in k["name"] or k["name"] in seen:
+        continue
+    seen.add(k["name"])
+    h = k["hdr"]; ia, ii, it, iss = h.index("Source"), h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("Warp Stall Sampling (All Samples)")
+    tot = sum(int(r[ii]) for r in k["rows"]); tott = sum(int(r[it]) for r in k["rows"]); tots = sum(int(r[iss]) for r in k["rows"]) or 1
+    print(f"### {k['name'].split('(const int *')[0]} — {tot / 1e9:.3f} G warp instructions, {tott / max(tot, 1):.1f} lanes\n")
+    print("| SASS line | instruction | executed | lanes | samples |\n|---|---|---|---|---|")
+    top = sorted(range(len(k["rows"])), key=lambda i: -int(k["rows"][i][iss]))[:8]
+    for i in sorted(top):
+        r = k["rows"][i]
+        ex = int(r[ii])
+        print(f"| {i} | `{r[ia].strip()[:60]}` | {ex / 1e6:.1f} M | {int(r[it]) / max(ex, 1):.0f} | {100 * int(r[iss]) / tots:.1f} % |")
+    print()

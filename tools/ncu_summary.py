@@ -13,7 +13,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "lts__t_sector_hit_rate.pct"]
-ALGO = {"binary_z_kernel": 5, "band_strided_kernel": 8}          # algorithmic bytes per voxel
+ALGO = {"binary_z_kernel": 5, "band_strided_kernel": 8, "line_hull_kernel": 8}          # algorithmic bytes per voxel
 NVOX = 1 << 30
 
 
@@ -72,7 +72,11 @@ def main():
     from bench import kernel_source_hash
     out = {"kernel_source_hash": kernel_source_hash(), "grid": "1024x1024x1024", "source": f"{rep} (ncu --set full, one launch per kernel)"}
     for name, b in traffic.items():
-        key = "pass1_z_ms" if "binary_z" in name else ("pass3_x_ms" if ("(bool)1" in name or ", 1>" in name) else "pass2_y_ms")
+        if "binary_z" in name: key = "pass1_z_ms"
+        elif "line_hull" in name:                    # line_hull_kernel<WIDE, FINAL, TPB>
+            flags = name.split("<")[1].split(">")[0].split(",")
+            key = "pass3_x_ms" if flags[1].strip() in ("(bool)1", "1", "true") else "pass2_y_ms"
+        else: key = "pass3_x_ms" if ("(bool)1" in name or ", 1>" in name) else "pass2_y_ms"    # band_strided_kernel<.., FINAL>
         out[key] = {"kernel": name.split("(")[0], "dram_bytes_per_launch": b}
     json.dump(out, open("/tmp/ncu_traffic.json", "w"), indent=1)
 
