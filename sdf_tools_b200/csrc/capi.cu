@@ -218,9 +218,10 @@ int sdf_b200_host_free(void* p)
 //   line  : both passes with the line-per-thread kernel (hull stacks in an L2-resident scratch field; 8-12 extra bytes
 //           per voxel); the y pass leaves its result x/y-swapped so that both passes read rows that are nz apart;
 //   mixed : line-per-thread y pass, banded x pass;
-//   auto  : mixed when one launch of the y pass has at least 2^19 lines of 512..1024 voxels with 32-bit stack entries
-//           (measured: with fewer or shorter lines the line kernel cannot fill the GPU with independent work, and with
-//           64-bit entries its stack traffic doubles -- the banded kernel is faster there), else band.
+//   auto  : the line kernel for a pass whose launch has enough lines of 512..1024 voxels with 32-bit stack entries -- 2^19
+//           for the y pass, 2^20 for the x pass (measured: with fewer or shorter lines the line kernel cannot fill the
+//           GPU with independent work, with 64-bit entries its stack traffic doubles, and the x pass with its deeper
+//           hulls needs more lines to win; the banded kernel is faster there) -- i.e. line, mixed or band.
 // A plan that needs scratch falls back to band when the scratch cannot be allocated.
 enum { HULL_AUTO = 0, HULL_BAND = 1, HULL_LINE = 2, HULL_MIXED = 3 };
 
@@ -247,10 +248,12 @@ static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int6
 {
     LinePlan P;
     int mode = ctx->hull_mode < 0 ? hull_default() : ctx->hull_mode;
+    const int64_t hz_all = (nz_total - 1) * (nz_total - 1), hy_all = (ny - 1) * (ny - 1);
     if (mode == HULL_AUTO) {
-        const int64_t lines = (x_per_launch > 0 ? x_per_launch : nx) * nz;
-        const bool narrow = (nz_total - 1) * (nz_total - 1) < (1 << 22);
-        mode = (lines >= (1 << 19) && ny >= 512 && ny <= 1024 && narrow) ? HULL_MIXED : HULL_BAND;
+        const int64_t lines_y = (x_per_launch > 0 ? x_per_launch : nx) * nz, lines_x = ny * nz;
+        const bool y_ok = lines_y >= (1 << 19) && ny >= 512 && ny <= 1024 && hz_all < (1 << 22);
+        const bool x_ok = x_per_launch == 0 && lines_x >= (1 << 20) && nx >= 512 && nx <= 1024 && hz_all + hy_all < (1 << 22);
+        mode = (y_ok && x_ok) ? HULL_LINE : (y_ok ? HULL_MIXED : HULL_BAND);
     }
     if (ny <= 1 && mode == HULL_MIXED) mode = HULL_BAND;        // no y pass
     if (mode == HULL_BAND) return P;

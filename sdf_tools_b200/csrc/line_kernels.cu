@@ -12,8 +12,15 @@
 
 namespace sdfb200 {
 
+// Resident threads per SM the register allocation must allow: 1536 (48 warps, 40 registers, a few spilled words) measured
+// best at 1024^3 -- 1280 (unconstrained, 48-56 registers): y / x pass 4.55 / 8.10 ms; 1536: 4.36 / 7.77; 1792-2048 (32
+// registers, heavy spills): 5.04 / 9.65.  The kernel is latency bound on its L2-resident stacks, so warps beat registers.
+#ifndef LH_THREADS_PER_SM
+#define LH_THREADS_PER_SM 1536
+#endif
+
 template <bool WIDE, bool FINAL, int TPB>
-__global__ void __launch_bounds__(TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+__global__ void __launch_bounds__(TPB, LH_THREADS_PER_SM / TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
                                                         typename LineEntry<WIDE>::type* __restrict__ stk, uint32_t* __restrict__ pol,
                                                         int n, int64_t line_stride, int64_t ncols, int64_t nlines, int64_t outer_stride,
                                                         int64_t out_stride, int64_t out_outer_stride,
@@ -76,6 +83,12 @@ static cudaError_t launch_line_tpb(const int32_t* in, void* out, void* stk, uint
     if (smem < 0) smem = line_knob("SDF_B200_LINE_SMEM", 0);
     if (smem > 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    static int carve = -2;         // SDF_B200_LINE_CARVE: preferred shared-memory carve-out in percent (experiments)
+    if (carve == -2) carve = line_knob("SDF_B200_LINE_CARVE", -1);
+    if (carve >= 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return e;
     }
     kern<<<(unsigned)blocks, TPB, smem, st>>>(in, (int32_t*)out, (typename LineEntry<WIDE>::type*)stk, pol, n, line_stride, ncols, nlines,
