@@ -262,10 +262,14 @@ static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int6
     P.wide_y = ny > 1024 || hz >= (1 << 22);
     P.wide_x = nx > 1024 || hz + hy >= (1 << 22);
     const int64_t polw_y = nx * ((ny + 31) / 32) * nz, polw_x = ((nx + 31) / 32) * ny * nz;
-    const bool wide = mode == HULL_LINE ? (P.wide_y || P.wide_x) : P.wide_y;
     const int64_t polw = mode == HULL_LINE ? (polw_y > polw_x ? polw_y : polw_x) : polw_y;
+    size_t stack_need = (size_t)sdfb200::line_stack_entries(ny, nx * nz) * (P.wide_y ? 8 : 4);
+    if (mode == HULL_LINE) {
+        const size_t sx = (size_t)sdfb200::line_stack_entries(nx, ny * nz) * (P.wide_x ? 8 : 4);
+        stack_need = sx > stack_need ? sx : stack_need;
+    }
     char keep[512]; memcpy(keep, ctx->err, sizeof(keep));
-    if (grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)N * 4) || grow(ctx, &ctx->d_stack, &ctx->stack_bytes, (size_t)N * (wide ? 8 : 4)) ||
+    if (grow(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)N * 4) || grow(ctx, &ctx->d_stack, &ctx->stack_bytes, stack_need) ||
         grow(ctx, &ctx->d_pol, &ctx->pol_bytes, (size_t)polw * 4)) {
         memcpy(ctx->err, keep, sizeof(keep));          // not an error: the in-place kernel needs no scratch
         return P;
@@ -753,7 +757,7 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         CK(sdfb200::launch_binary_z(d_mask + off, (LP.mode == HULL_MIXED ? tmp : d_field) + off, (int)nz, (x1 - x0) * ny, nullptr, st),
            "launch binary_z");
         ctx->launches++;
-        char* stack_y = (char*)ctx->d_stack + (size_t)off * (LP.wide_y ? 8 : 4);
+        void* stack_y = ctx->d_stack;                               // dead after each launch: every chunk reuses it
         uint32_t* pol_y = (uint32_t*)ctx->d_pol + x0 * nwy * nz;
         if (LP.mode == HULL_LINE)            // x-chunk of the y pass: field[x0..x1) -> tmp[y][x0..x1)[z]
             CK(sdfb200::launch_line_hull(d_field + off, tmp + x0 * nz, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nx * nz, nz, LP.wide_y,
@@ -771,7 +775,7 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         if (y1 == y0) continue;
         const int64_t col0 = y0 * nz, ncols = (y1 - y0) * nz;
         if (LP.mode == HULL_LINE)            // y-chunk of the x pass: tmp[y0..y1) -> field[.][y0..y1)[z]
-            CK(sdfb200::launch_line_hull(tmp + y0 * nx * nz, d_field + col0, (char*)ctx->d_stack + (size_t)(y0 * nx * nz) * (LP.wide_x ? 8 : 4),
+            CK(sdfb200::launch_line_hull(tmp + y0 * nx * nz, d_field + col0, ctx->d_stack,
                                          (uint32_t*)ctx->d_pol + y0 * nwx * nz, (int)nx, nz, nz, y1 - y0, nx * nz, plane, nz, LP.wide_x, true,
                                          res, ctx->d_ext, ctx->d_lut, LUT_N, st), "launch line_hull(x)");
         else

@@ -67,6 +67,26 @@ template <> struct LineEntry<true> {
     static SDF_HD int32_t h(type e) { return (int32_t)(e & 0xffffffffull); }
 };
 
+// Stack layout.  The 32 lines of a warp share one block of n x 32 entries; slot s of lane l lives at
+//     (s / C) * 32 * C  +  l * C  +  s % C            C = LH_CHUNK = 4
+// i.e. C consecutive slots of ONE line are contiguous (16 bytes with 32-bit entries: a 32-byte sector belongs to two
+// neighbouring lines, a 128-byte cache line to eight), and a warp whose lanes sit at similar depths touches four or so
+// cache lines per access.  A line's own pushes, pops and fetches therefore keep hitting the sector they just used (the
+// hull fetches of the query sweep walk a lane's slots in order), instead of sharing every sector with seven other lines
+// that want it at different times, as the plain [slot][line] layout does.  Measured at 1024^3 (y / x pass, ms):
+// C = 1: 4.36 / 7.77, C = 2: 4.20 / 7.12, C = 4: 4.08 / 6.87, C = 8: 4.14 / 7.05, C = 16: 4.24 / 7.25; DRAM traffic of the
+// x pass 2.07 -> 1.5 x the algorithmic bytes, L1 hit rate 68 -> 81 %.  `stk` below is the lane's slot 0: block base + l * C.
+#ifndef LH_U
+#define LH_U 4
+#endif
+#ifndef LH_CHUNK_LOG
+#define LH_CHUNK_LOG 2
+#endif
+constexpr int LH_CHUNK = 1 << LH_CHUNK_LOG;          // consecutive slots of one line that are contiguous in memory
+template <typename T> SDF_HD T* lh_slot(T* stk, int s) { return stk + ((s & ~(LH_CHUNK - 1)) << 5) + (s & (LH_CHUNK - 1)); }
+SDF_HD int64_t lh_block_entries(int n) { return (int64_t)32 * ((n + LH_CHUNK - 1) & ~(LH_CHUNK - 1)); }   // stack block of one warp
+SDF_HD int lh_lane_offset(int lane) { return lane * LH_CHUNK; }
+
 // t on or above the chord s->u of the lifted points  <=>  parabola t never wins
 SDF_HD bool lh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t uY) {
     const long long lhs = (long long)(tY - sY) * (long long)(up - tp);
@@ -82,7 +102,7 @@ SDF_HD bool lh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t
 #define LH_CTZ(x) __builtin_ctz(x)
 #endif
 
-// One line.  in / stk: element 0 of the line, consecutive positions `stride` elements apart (stk in entries);
+// One line.  in: element 0 of the line, consecutive positions `stride` elements apart; stk: the lane's slot 0 (above);
 // pol: word 0 of the line's polarity bits, consecutive words `pstride` elements apart.  emit(m, neg) receives the
 // squared distance m (<= SDF_INF) and the polarity of positions 0, 1, .. n-1 in order.
 //
@@ -111,18 +131,17 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
         int tp = bpos; int32_t tY = bY;              // T: top of the chain
         int sp = tp; int32_t sY = tY + 1;            // S: below T, or the none-sentinel (sp == tp: the hull test is false)
         ent_t R = 0;                                 // v_{d-3} when it exists
-        ent_t* top = stk;                            // slot a + d
-        const int64_t stride3 = 3 * stride;
+        int ts = 0;                                  // slot a + d (next push)
         bool prevpol = in[0] < 0;
         auto pop_against = [&](int qp, int32_t qY) {
             while (lh_dominated(sp, sY, tp, tY, qp, qY)) {
                 LH_TICK(2);
                 --d;
-                top -= stride;
+                --ts;
                 tp = sp; tY = sY;
                 if (d >= 2) {
                     sp = E::pos(R); sY = sp * sp + E::h(R);                  // v_{d-2}
-                    if (d >= 3) R = *(top - stride3);                        // v_{d-3}
+                    if (d >= 3) R = *lh_slot(stk, ts - 3);                        // v_{d-3}
                 } else if (d == 1) { sp = bpos; sY = bY; }
                 else { sp = tp; sY = tY + 1; }                               // T is the boundary site: nothing below
             }
@@ -132,11 +151,11 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
             if (p != prevpol) {                      // a run ends at y-1 and the next starts at y
                 LH_TICK(3);
                 pop_against(y, y * y);               // close against the right boundary site (y, 0)
-                if (d < y - a) *top = E::term();
+                if (d < y - a) *lh_slot(stk, ts) = E::term();
                 a = y; d = 0;
                 bpos = y - 1; bY = bpos * bpos;
                 tp = bpos; tY = bY; sp = tp; sY = tY + 1;
-                top = stk + (int64_t)y * stride;
+                ts = y;
                 prevpol = p;
             }
             const int32_t h = p ? -v : v;
@@ -144,15 +163,15 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 LH_TICK(1);
                 const int32_t Y = y * y + h;
                 pop_against(y, Y);
-                *top = E::pack(y, h);
-                top += stride;
+                *lh_slot(stk, ts) = E::pack(y, h);
+                ++ts;
                 ++d;
                 R = E::pack(sp, sY - sp * sp);       // (garbage when S is not a vertex: then never used)
                 sp = tp; sY = tY;
                 tp = y; tY = Y;
             }
         };
-        constexpr int U = 4;                         // rows read ahead of the (data-dependent) stack work
+        constexpr int U = LH_U;                      // rows read ahead of the (data-dependent) stack work
         const int32_t* ip = in;
         uint32_t* pp = pol;
         uint32_t pw = 0;
@@ -185,7 +204,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
             }
             if ((y0 & 31) == 32 - U || y0 + U >= n) { *pp = pw; pp += pstride; pw = 0; }
         }
-        if (d < n - a) *top = E::term();             // the last run has no right boundary site
+        if (d < n - a) *lh_slot(stk, ts) = E::term();  // the last run has no right boundary site
     }
     // ------------------------------------------------------------------------------------------------ query sweep
     {
@@ -193,7 +212,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
         int cpos = 0, npos = 0;                      // current / next point of the run's hull (vertex or boundary site)
         int32_t ch = BIG, nh = NOSITE;
         ent_t NE = E::term();                        // the stack entry after `next`, fetched ahead (terminator: none)
-        const ent_t* fp = stk;                       // slot after NE's
+        int fs = 0;                                  // slot after NE's
         int left = 0;                                // slots of the run not fetched yet
         bool tail = true, neg = false;
         // next <- the point after it: the entry fetched ahead, then the right boundary site (e, 0), then nothing
@@ -202,7 +221,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
             if (!E::is_term(NE)) {
                 npos = E::pos(NE); nh = E::h(NE);
                 NE = E::term();
-                if (left > 0) { NE = *fp; fp += stride; --left; }
+                if (left > 0) { NE = *lh_slot(stk, fs); ++fs; --left; }
             } else if (!tail) { tail = true; npos = e; nh = (e < n) ? 0 : NOSITE; }
             else nh = NOSITE;
         };
@@ -220,9 +239,9 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                     while (!x && ++w2 < nw) { const uint32_t q = *p2; p2 += pstride; x = neg ? ~q : q; }
                     e = x ? (w2 << 5) + LH_CTZ(x) : n;
                     if (e > n) e = n;                // (the bits past the end of the line are zero)
-                    fp = stk + (int64_t)y * stride;
+                    fs = y;
                     left = e - y;
-                    NE = *fp; fp += stride; --left;  // (left >= 1 here)
+                    NE = *lh_slot(stk, fs); ++fs; --left;  // (left >= 1 here)
                     tail = false;
                     npos = y - 1; nh = y > 0 ? 0 : BIG;       // the left boundary site becomes `current` ...
                     advance();                       // ... and the first vertex (or the right boundary site) `next`

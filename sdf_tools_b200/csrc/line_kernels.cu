@@ -37,7 +37,10 @@ __global__ void __launch_bounds__(TPB, LH_THREADS_PER_SM / TPB) line_hull_kernel
         // final pass: the table load of one position is issued a whole position before its result is stored
         float fpend = 0.f;
         bool negpend = false, first = true;
-        line_hull_pass<WIDE>(in + base, line_stride, n, stk + base, pol + outer * (int64_t)nw * ncols + col, ncols,
+        // the warp's block of the stack scratch, then this lane's slot 0 inside it (line_hull.cuh, "Stack layout")
+        const int lane = threadIdx.x & 31;
+        typename LineEntry<WIDE>::type* my_stk = stk + (lid >> 5) * lh_block_entries(n) + lh_lane_offset(lane);
+        line_hull_pass<WIDE>(in + base, line_stride, n, my_stk, pol + outer * (int64_t)nw * ncols + col, ncols,
             [&](int32_t m, bool neg) {
                 if (FINAL) {
                     if (neg) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);

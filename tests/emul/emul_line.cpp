@@ -11,12 +11,14 @@ static void pass_lines(const int32_t* in, int32_t* out, int n, int64_t line_stri
 {
     typedef typename LineEntry<WIDE>::type ent_t;
     const int nw = (n + 31) / 32;
-    std::vector<ent_t> stk((size_t)n * ncols, (ent_t)0x12345678);        // stale garbage: the pass must not depend on it
+    const int64_t tiles = (ncols + 31) / 32;
+    std::vector<ent_t> stk((size_t)tiles * lh_block_entries(n), (ent_t)0x12345678);   // stale garbage: the pass must not depend on it
     std::vector<uint32_t> pol((size_t)nw * ncols, 0xdeadbeefu);
-    for (int64_t c = 0; c < ncols; c++)
-    {
+    const int64_t tile_elems = lh_block_entries(n);
+    for (int64_t c = 0; c < ncols; c++) {
         int32_t* dst = out + c;
-        line_hull_pass<WIDE>(in + c, line_stride, n, stk.data() + c, pol.data() + c, ncols,
+        const int l = (int)(c & 31);
+        line_hull_pass<WIDE>(in + c, line_stride, n, stk.data() + (c >> 5) * tile_elems + lh_lane_offset(l), pol.data() + c, ncols,
                              [&](int32_t m, bool neg) { *dst = neg ? -m : m; dst += line_stride; });
     }
 }
