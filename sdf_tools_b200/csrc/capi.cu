@@ -872,7 +872,6 @@ int sdf_b200_slab_summary_scatter_device(sdf_b200_ctx* ctx, const uint8_t* d_mas
 
 int sdf_b200_create_multi(sdf_b200_ctx** out, const int* devices, int ndev)
 {
-    sdf_b200_ctx* ctx = nullptr;                      // for fail()
     if (!out) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create_multi: out is NULL");
     *out = nullptr;
     if (!devices || ndev < 1 || ndev > SDF_MAX_PEERS) return fail(nullptr, SDF_B200_ERR_ARG, "sdf_b200_create_multi: bad device list");

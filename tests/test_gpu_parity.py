@@ -221,8 +221,10 @@ def test_c3_full_size_1024(ctx):
     want_s = O.signed_d2(mask)                                     # ONE oracle run (two exact EDTs, all cores)
     got_s = gpu_signed_d2(ctx, mask)
     assert np.array_equal(got_s, want_s), f"P1 failed: {(got_s != want_s).sum()} voxels differ"
+    assert ctx.last_envelope_kernel() == "line"                     # this size: the line-per-thread kernel on both passes
     del got_s
     got, (gmx, gmn) = ctx.build_from_mask(mask, res)              # >= 2^25 voxels: the chunked, copy-overlapped path
+    assert ctx.last_envelope_kernel() == "band"                     # its x-chunks are too small for the line kernel
     assert np.array_equal(np.signbit(got), mask != 0), "P0 failed"
     # the combine loop (sdf_generation.hpp:254-265) applied to the oracle's integers, chunk by chunk
     wmx, wmn = -np.inf, np.inf
@@ -232,6 +234,15 @@ def test_c3_full_size_1024(ctx):
         assert np.array_equal(got[x0:x0 + 64].view(np.uint32), d.astype(np.float32).view(np.uint32)), "P2 failed"
         wmx, wmn = max(wmx, d.max()), min(wmn, d.min())
     assert (gmx, gmn) == (wmx, wmn), "P4 failed"
+    # the device-resident build (what bench.py times: line-per-thread kernels incl. the fused distance epilogue)
+    m = torch.from_numpy(mask).cuda()
+    out = torch.empty(mask.shape, dtype=torch.float32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.build_device(m.data_ptr(), *mask.shape, res, out.data_ptr())
+    torch.cuda.synchronize()
+    assert ctx.last_envelope_kernel() == "line"
+    assert ctx.get_extrema() == (gmx, gmn)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), got.view(np.uint32)), "device-resident build differs from the host path"
 
 
 @pytest.mark.skipif(_mem_gb() < 40, reason="needs ~20 GB of host memory (the reference holds ~108 B/voxel)")
