@@ -71,8 +71,9 @@ int sdf_b200_synchronize(sdf_b200_ctx* ctx);
 
 /* Kernels of the two strided envelope passes (the per-axis loops of BuildDistanceField, sdf_generation.hpp:95-207; no
  * counterpart in the reference -- results are identical in every mode):
- *   0 auto  : mixed for grids whose y pass has >= 2^20 lines of >= 512 voxels, else band (default; the environment
- *             variable SDF_B200_HULL=band|line|mixed|auto changes the default of contexts that never call this);
+ *   0 auto  : per pass, the line kernel when its launch has several hundred thousand lines of >= 512 voxels whose hull
+ *             entries fit 32 bits, else the banded kernel (default; the environment variable
+ *             SDF_B200_HULL=band|line|mixed|auto changes the default of contexts that never call this);
  *   1 band  : in-place banded kernel, hull stacks in shared memory, no scratch;
  *   2 line  : one thread per line for both passes, hull stacks in a device scratch (8-12 extra bytes per voxel);
  *   3 mixed : line-per-thread y pass, banded x pass (4-12 extra bytes per voxel).

@@ -218,10 +218,11 @@ int sdf_b200_host_free(void* p)
 //   line  : both passes with the line-per-thread kernel (hull stacks in an L2-resident scratch field; 8-12 extra bytes
 //           per voxel); the y pass leaves its result x/y-swapped so that both passes read rows that are nz apart;
 //   mixed : line-per-thread y pass, banded x pass;
-//   auto  : the line kernel for a pass whose launch has enough lines of 512..1024 voxels with 32-bit stack entries -- 2^19
-//           for the y pass, 2^20 for the x pass (measured: with fewer or shorter lines the line kernel cannot fill the
-//           GPU with independent work, with 64-bit entries its stack traffic doubles, and the x pass with its deeper
-//           hulls needs more lines to win; the banded kernel is faster there) -- i.e. line, mixed or band.
+//   auto  : the line kernel for a pass whose launch has enough lines of >= 512 voxels with 32-bit stack entries -- 2^19
+//           for a y pass of up to 1024 voxels per line, 2^20 for longer y lines and for the x pass (measured: with fewer
+//           or shorter lines the line kernel cannot fill the GPU with independent work, with 64-bit entries its stack
+//           traffic doubles, and deeper hulls need more lines to win; the banded kernel is faster there) -- i.e. line,
+//           mixed or band.
 // A plan that needs scratch falls back to band when the scratch cannot be allocated.
 enum { HULL_AUTO = 0, HULL_BAND = 1, HULL_LINE = 2, HULL_MIXED = 3 };
 
@@ -240,7 +241,7 @@ static int hull_default()
 
 struct LinePlan {
     int mode = HULL_BAND;                  // resolved: HULL_BAND, HULL_LINE or HULL_MIXED
-    bool wide_y = false, wide_x = false;   // 64-bit stack entries (line longer than 1024 or heights >= 2^22)
+    int fmt_y = 0, fmt_x = 0;              // stack entry formats of the two passes (line_entry_format)
 };
 
 // Decide the kernels for a grid and size the scratch.  nz_total: the whole z extent the binary pass saw (slab builds).
@@ -248,24 +249,23 @@ static LinePlan plan_line_passes(sdf_b200_ctx* ctx, int64_t nx, int64_t ny, int6
 {
     LinePlan P;
     int mode = ctx->hull_mode < 0 ? hull_default() : ctx->hull_mode;
-    const int64_t hz_all = (nz_total - 1) * (nz_total - 1), hy_all = (ny - 1) * (ny - 1);
+    const int64_t hz = (nz_total - 1) * (nz_total - 1), hy = (ny - 1) * (ny - 1);     // largest heights the y / x pass can meet: hz, hz + hy
+    P.fmt_y = sdfb200::line_entry_format(ny, hz);
+    P.fmt_x = sdfb200::line_entry_format(nx, hz + hy);
     if (mode == HULL_AUTO) {
         const int64_t lines_y = (x_per_launch > 0 ? x_per_launch : nx) * nz, lines_x = ny * nz;
-        const bool y_ok = lines_y >= (1 << 19) && ny >= 512 && ny <= 1024 && hz_all < (1 << 22);
-        const bool x_ok = x_per_launch == 0 && lines_x >= (1 << 20) && nx >= 512 && nx <= 1024 && hz_all + hy_all < (1 << 22);
+        const bool y_ok = lines_y >= (ny <= 1024 ? (1 << 19) : (1 << 20)) && ny >= 512 && sdfb200::line_entry_bytes(P.fmt_y) == 4;
+        const bool x_ok = x_per_launch == 0 && lines_x >= (1 << 20) && nx >= 512 && sdfb200::line_entry_bytes(P.fmt_x) == 4;
         mode = (y_ok && x_ok) ? HULL_LINE : (y_ok ? HULL_MIXED : HULL_BAND);
     }
     if (ny <= 1 && mode == HULL_MIXED) mode = HULL_BAND;        // no y pass
     if (mode == HULL_BAND) return P;
     const int64_t N = nx * ny * nz;
-    const int64_t hz = (nz_total - 1) * (nz_total - 1), hy = (ny - 1) * (ny - 1);
-    P.wide_y = ny > 1024 || hz >= (1 << 22);
-    P.wide_x = nx > 1024 || hz + hy >= (1 << 22);
     const int64_t polw_y = nx * ((ny + 31) / 32) * nz, polw_x = ((nx + 31) / 32) * ny * nz;
     const int64_t polw = mode == HULL_LINE ? (polw_y > polw_x ? polw_y : polw_x) : polw_y;
-    size_t stack_need = (size_t)sdfb200::line_stack_entries(ny, nx * nz) * (P.wide_y ? 8 : 4);
+    size_t stack_need = (size_t)sdfb200::line_stack_entries(ny, nx * nz) * sdfb200::line_entry_bytes(P.fmt_y);
     if (mode == HULL_LINE) {
-        const size_t sx = (size_t)sdfb200::line_stack_entries(nx, ny * nz) * (P.wide_x ? 8 : 4);
+        const size_t sx = (size_t)sdfb200::line_stack_entries(nx, ny * nz) * sdfb200::line_entry_bytes(P.fmt_x);
         stack_need = sx > stack_need ? sx : stack_need;
     }
     char keep[512]; memcpy(keep, ctx->err, sizeof(keep));
@@ -307,10 +307,10 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
     CK(cudaEventRecord(ctx->ev[1], st), "event");
     if (ny > 1) {
         if (LP.mode == HULL_LINE)            // field[x][y][z] -> tmp[y][x][z]
-            CK(sdfb200::launch_line_hull(d_field, tmp, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nx * nz, nz, LP.wide_y,
+            CK(sdfb200::launch_line_hull(d_field, tmp, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nx * nz, nz, LP.fmt_y,
                                          false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
         else if (LP.mode == HULL_MIXED)      // tmp[x][y][z] -> field[x][y][z]
-            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nz, ny * nz, LP.wide_y,
+            CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)ny, nz, nz, nx, ny * nz, nz, ny * nz, LP.fmt_y,
                                          false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
         else
             CK(sdfb200::launch_band_strided(d_field, (int)ny, nz, nz, nx, ny * nz, false, res, ctx->d_ext, ctx->d_dbg, nullptr, 0, st),
@@ -319,7 +319,7 @@ static int run_passes(sdf_b200_ctx* ctx, const uint8_t* d_mask, int64_t nx, int6
     }
     CK(cudaEventRecord(ctx->ev[2], st), "event");
     if (LP.mode == HULL_LINE)                // tmp[y][x][z] -> field[x][y][z]
-        CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, nz, nz, ny, nx * nz, ny * nz, nz, LP.wide_x,
+        CK(sdfb200::launch_line_hull(tmp, d_field, ctx->d_stack, (uint32_t*)ctx->d_pol, (int)nx, nz, nz, ny, nx * nz, ny * nz, nz, LP.fmt_x,
                                      final_pass, res, ctx->d_ext, final_pass ? ctx->d_lut : nullptr, final_pass ? LUT_N : 0, st),
            "launch line_hull(x)");
     else
@@ -760,10 +760,10 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         void* stack_y = ctx->d_stack;                               // dead after each launch: every chunk reuses it
         uint32_t* pol_y = (uint32_t*)ctx->d_pol + x0 * nwy * nz;
         if (LP.mode == HULL_LINE)            // x-chunk of the y pass: field[x0..x1) -> tmp[y][x0..x1)[z]
-            CK(sdfb200::launch_line_hull(d_field + off, tmp + x0 * nz, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nx * nz, nz, LP.wide_y,
+            CK(sdfb200::launch_line_hull(d_field + off, tmp + x0 * nz, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nx * nz, nz, LP.fmt_y,
                                          false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
         else if (LP.mode == HULL_MIXED)      // tmp[x0..x1) -> field[x0..x1)
-            CK(sdfb200::launch_line_hull(tmp + off, d_field + off, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nz, plane, LP.wide_y,
+            CK(sdfb200::launch_line_hull(tmp + off, d_field + off, stack_y, pol_y, (int)ny, nz, nz, x1 - x0, plane, nz, plane, LP.fmt_y,
                                          false, res, ctx->d_ext, nullptr, 0, st), "launch line_hull(y)");
         else
             CK(sdfb200::launch_band_strided(d_field + off, (int)ny, nz, nz, x1 - x0, plane, false, res, ctx->d_ext, nullptr,
@@ -776,7 +776,7 @@ static int build_host_pipelined(sdf_b200_ctx* ctx, const void* h_in, bool is_cel
         const int64_t col0 = y0 * nz, ncols = (y1 - y0) * nz;
         if (LP.mode == HULL_LINE)            // y-chunk of the x pass: tmp[y0..y1) -> field[.][y0..y1)[z]
             CK(sdfb200::launch_line_hull(tmp + y0 * nx * nz, d_field + col0, ctx->d_stack,
-                                         (uint32_t*)ctx->d_pol + y0 * nwx * nz, (int)nx, nz, nz, y1 - y0, nx * nz, plane, nz, LP.wide_x, true,
+                                         (uint32_t*)ctx->d_pol + y0 * nwx * nz, (int)nx, nz, nz, y1 - y0, nx * nz, plane, nz, LP.fmt_x, true,
                                          res, ctx->d_ext, ctx->d_lut, LUT_N, st), "launch line_hull(x)");
         else
             CK(sdfb200::launch_band_strided(d_field + col0, (int)nx, plane, ncols, 1, 0, true, res, ctx->d_ext, nullptr,

@@ -41,12 +41,14 @@ cudaError_t launch_band_strided(int32_t* g, int n, int64_t line_stride, int64_t 
 // K2/K3, line-per-thread variant (line_kernels.cu): OUT OF PLACE.  Line (outer, col), col < ncols contiguous:
 //        input position y at in[outer*outer_stride + col + y*line_stride], result at out[outer*out_outer_stride + col +
 //        y*out_stride] (so a pass can also re-order the axes); hull stacks in d_stack: line_stack_entries(n, lines)
-//        entries of 4 bytes, or 8 with wide_entries -- required when n > 1024 or a height can reach 2^22 (dead after
-//        the launch: every launch may use the same scratch); one polarity bit per voxel in d_pol (nouter x ceil(n/32) x
-//        ncols words).
+//        entries of line_entry_bytes(entry_format) bytes, entry_format = line_entry_format(n, largest height the pass can
+//        meet) (dead after the launch: every launch may use the same scratch); one polarity bit per voxel in d_pol
+//        (nouter x ceil(n/32) x ncols words).
+int line_entry_format(int64_t n, int64_t hmax);     // 0: {pos:10,h:22}  1: {pos:11,h:21}  2: 64-bit entries
+int line_entry_bytes(int entry_format);
 inline int64_t line_stack_entries(int64_t n, int64_t lines) { return ((lines + 31) / 32) * 32 * ((n + 15) / 16 * 16); }
 cudaError_t launch_line_hull(const int32_t* in, void* out, void* d_stack, uint32_t* d_pol, int n, int64_t line_stride, int64_t ncols,
-                             int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, bool wide_entries,
+                             int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, int entry_format,
                              bool final_pass, double res, int* d_ext, const float* d_lut, int lut_n, cudaStream_t st);
 
 // d_lut[m] = (float)(sqrt((double)m) * res), m < n: the final pass's exact distance table for one resolution

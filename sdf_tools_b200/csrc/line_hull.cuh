@@ -46,19 +46,22 @@ static long long lh_counters[8];   // 0 sites, 1 finite, 2 pops, 3 runs, 4 query
 #define LH_TICK(x) ((void)0)
 #endif
 
-// Stack entries: 32 bits {position : 10, height : 22} when the line has <= 1024 positions and heights stay below 2^22,
-// else 64 bits {position, height}.
-template <bool WIDE> struct LineEntry;
-template <> struct LineEntry<false> {
+// Stack entries, three formats: 32 bits {position : 10, height : 22} for lines of <= 1024 positions whose heights stay
+// below 2^22, 32 bits {position : 11, height : 21} for lines of <= 2048 positions with heights below 2^21, else 64 bits
+// {position, height}.  The all-ones word is the terminator: a 32-bit format is only chosen when every height stays below
+// its all-ones height field, so no vertex can look like it.
+enum { LH_FMT_P10 = 0, LH_FMT_P11 = 1, LH_FMT_WIDE = 2 };
+template <int FMT> struct LineEntry {               // the two 32-bit formats
+    static constexpr int HBITS = FMT == LH_FMT_P10 ? 22 : 21;
     typedef uint32_t type;
     static constexpr uint32_t TERM = 0xffffffffu;
-    static SDF_HD type pack(int pos, int32_t h) { return ((uint32_t)pos << 22) | (uint32_t)h; }
+    static SDF_HD type pack(int pos, int32_t h) { return ((uint32_t)pos << HBITS) | (uint32_t)h; }
     static SDF_HD bool is_term(type e) { return e == TERM; }
     static SDF_HD type term() { return TERM; }
-    static SDF_HD int pos(type e) { return (int)(e >> 22); }
-    static SDF_HD int32_t h(type e) { return (int32_t)(e & 0x3fffffu); }
+    static SDF_HD int pos(type e) { return (int)(e >> HBITS); }
+    static SDF_HD int32_t h(type e) { return (int32_t)(e & ((1u << HBITS) - 1u)); }
 };
-template <> struct LineEntry<true> {
+template <> struct LineEntry<LH_FMT_WIDE> {
     typedef unsigned long long type;
     static SDF_HD type pack(int pos, int32_t h) { return ((unsigned long long)(uint32_t)pos << 32) | (uint32_t)h; }
     static SDF_HD bool is_term(type e) { return (e >> 32) == 0xffffffffull; }
@@ -66,6 +69,13 @@ template <> struct LineEntry<true> {
     static SDF_HD int pos(type e) { return (int)(e >> 32); }
     static SDF_HD int32_t h(type e) { return (int32_t)(e & 0xffffffffull); }
 };
+// the narrowest format that holds lines of n positions with heights <= hmax
+SDF_HD int lh_entry_format(int64_t n, int64_t hmax)
+{
+    if (n <= 1024 && hmax < (1 << 22) - 1) return LH_FMT_P10;
+    if (n <= 2048 && hmax < (1 << 21) - 1) return LH_FMT_P11;
+    return LH_FMT_WIDE;
+}
 
 // Stack layout.  The 32 lines of a warp share one block of n x 32 entries; slot s of lane l lives at
 //     (s / C) * 32 * C  +  l * C  +  s % C            C = LH_CHUNK = 4
@@ -115,11 +125,11 @@ SDF_HD bool lh_dominated(int sp, int32_t sY, int tp, int32_t tY, int up, int32_t
 // (Variants that were measured and dropped, see DESIGN.md: a shared-memory ring for the top of the stack, write-back
 // instead of write-through pushes, an asynchronous-copy FIFO for the query sweep.  Each removed stalls or L2 traffic
 // but cost more issue slots than it saved; this kernel is issue-bound.)
-template <bool WIDE, typename Emit>
-SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n, typename LineEntry<WIDE>::type* __restrict__ stk,
+template <int FMT, typename Emit>
+SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n, typename LineEntry<FMT>::type* __restrict__ stk,
                            uint32_t* __restrict__ pol, int64_t pstride, Emit emit)
 {
-    typedef LineEntry<WIDE> E;
+    typedef LineEntry<FMT> E;
     typedef typename E::type ent_t;
     constexpr int32_t BIG = 0x40000000;              // height of the "nothing on the left" boundary site
     constexpr int32_t NOSITE = 0x60000000;           // height of a non-existent next point: never wins

@@ -8,7 +8,6 @@
 // written once; stack traffic stays in L2 except for the long-lived part of a hull.
 #include "edt_kernels.cuh"
 #include "line_hull.cuh"
-#include <stdlib.h>
 
 namespace sdfb200 {
 
@@ -19,9 +18,9 @@ namespace sdfb200 {
 #define LH_THREADS_PER_SM 1536
 #endif
 
-template <bool WIDE, bool FINAL, int TPB>
+template <int FMT, bool FINAL, int TPB>
 __global__ void __launch_bounds__(TPB, LH_THREADS_PER_SM / TPB) line_hull_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
-                                                        typename LineEntry<WIDE>::type* __restrict__ stk, uint32_t* __restrict__ pol,
+                                                        typename LineEntry<FMT>::type* __restrict__ stk, uint32_t* __restrict__ pol,
                                                         int n, int64_t line_stride, int64_t ncols, int64_t nlines, int64_t outer_stride,
                                                         int64_t out_stride, int64_t out_outer_stride,
                                                         double res, int* __restrict__ ext, const float* __restrict__ lut, int lut_n)
@@ -39,8 +38,8 @@ __global__ void __launch_bounds__(TPB, LH_THREADS_PER_SM / TPB) line_hull_kernel
         bool negpend = false, first = true;
         // the warp's block of the stack scratch, then this lane's slot 0 inside it (line_hull.cuh, "Stack layout")
         const int lane = threadIdx.x & 31;
-        typename LineEntry<WIDE>::type* my_stk = stk + (lid >> 5) * lh_block_entries(n) + lh_lane_offset(lane);
-        line_hull_pass<WIDE>(in + base, line_stride, n, my_stk, pol + outer * (int64_t)nw * ncols + col, ncols,
+        typename LineEntry<FMT>::type* my_stk = stk + (lid >> 5) * lh_block_entries(n) + lh_lane_offset(lane);
+        line_hull_pass<FMT>(in + base, line_stride, n, my_stk, pol + outer * (int64_t)nw * ncols + col, ncols,
             [&](int32_t m, bool neg) {
                 if (FINAL) {
                     if (neg) maxneg = max(maxneg, m); else maxpos = max(maxpos, m);
@@ -67,60 +66,35 @@ __global__ void __launch_bounds__(TPB, LH_THREADS_PER_SM / TPB) line_hull_kernel
     }
 }
 
-static int line_knob(const char* name, int dflt)
-{
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
-
-template <bool WIDE, bool FINAL, int TPB>
-static cudaError_t launch_line_tpb(const int32_t* in, void* out, void* stk, uint32_t* pol, int n, int64_t line_stride, int64_t ncols,
-                                   int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, double res, int* ext, const float* lut,
-                                   int lut_n, cudaStream_t st)
-{
-    const int64_t nlines = ncols * nouter;
-    const int64_t blocks = (nlines + TPB - 1) / TPB;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    auto kern = line_hull_kernel<WIDE, FINAL, TPB>;
-    static int smem = -1;          // SDF_B200_LINE_SMEM: unused dynamic shared memory per block, to cap the resident warps (experiments)
-    if (smem < 0) smem = line_knob("SDF_B200_LINE_SMEM", 0);
-    if (smem > 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-    }
-    static int carve = -2;         // SDF_B200_LINE_CARVE: preferred shared-memory carve-out in percent (experiments)
-    if (carve == -2) carve = line_knob("SDF_B200_LINE_CARVE", -1);
-    if (carve >= 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e != cudaSuccess) return e;
-    }
-    kern<<<(unsigned)blocks, TPB, smem, st>>>(in, (int32_t*)out, (typename LineEntry<WIDE>::type*)stk, pol, n, line_stride, ncols, nlines,
-                                             outer_stride, out_stride, out_outer_stride, res, ext, lut, lut_n);
-    return cudaGetLastError();
-}
-
-template <bool WIDE, bool FINAL>
+template <int FMT, bool FINAL>
 static cudaError_t launch_line_cfg(const int32_t* in, void* out, void* stk, uint32_t* pol, int n, int64_t line_stride, int64_t ncols,
                                    int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, double res, int* ext, const float* lut,
                                    int lut_n, cudaStream_t st)
 {
-    if (ncols * nouter <= 0 || n <= 0) return cudaSuccess;
-    static int tpb = -1;
-    if (tpb < 0) tpb = line_knob("SDF_B200_LINE_TPB", 128);
-    if (tpb == 64) return launch_line_tpb<WIDE, FINAL, 64>(in, out, stk, pol, n, line_stride, ncols, nouter, outer_stride, out_stride, out_outer_stride, res, ext, lut, lut_n, st);
-    if (tpb == 256) return launch_line_tpb<WIDE, FINAL, 256>(in, out, stk, pol, n, line_stride, ncols, nouter, outer_stride, out_stride, out_outer_stride, res, ext, lut, lut_n, st);
-    return launch_line_tpb<WIDE, FINAL, 128>(in, out, stk, pol, n, line_stride, ncols, nouter, outer_stride, out_stride, out_outer_stride, res, ext, lut, lut_n, st);
+    constexpr int TPB = 128;
+    const int64_t nlines = ncols * nouter;
+    if (nlines <= 0 || n <= 0) return cudaSuccess;
+    const int64_t blocks = (nlines + TPB - 1) / TPB;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    line_hull_kernel<FMT, FINAL, TPB><<<(unsigned)blocks, TPB, 0, st>>>(in, (int32_t*)out, (typename LineEntry<FMT>::type*)stk, pol, n, line_stride, ncols,
+                                                                      nlines, outer_stride, out_stride, out_outer_stride, res, ext, lut, lut_n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_line_hull(const int32_t* in, void* out, void* d_stack, uint32_t* d_pol, int n, int64_t line_stride, int64_t ncols,
-                             int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, bool wide_entries,
+                             int64_t nouter, int64_t outer_stride, int64_t out_stride, int64_t out_outer_stride, int entry_format,
                              bool final_pass, double res, int* d_ext, const float* d_lut, int lut_n, cudaStream_t st)
 {
-    if (!wide_entries && n > 1024) return cudaErrorInvalidValue;
+    if ((entry_format == LH_FMT_P10 && n > 1024) || (entry_format == LH_FMT_P11 && n > 2048) || entry_format < 0 || entry_format > LH_FMT_WIDE)
+        return cudaErrorInvalidValue;
 #define LH_ARGS in, out, d_stack, d_pol, n, line_stride, ncols, nouter, outer_stride, out_stride, out_outer_stride, res, d_ext, d_lut, lut_n, st
-    if (wide_entries) return final_pass ? launch_line_cfg<true, true>(LH_ARGS) : launch_line_cfg<true, false>(LH_ARGS);
-    return final_pass ? launch_line_cfg<false, true>(LH_ARGS) : launch_line_cfg<false, false>(LH_ARGS);
+    if (entry_format == LH_FMT_WIDE) return final_pass ? launch_line_cfg<LH_FMT_WIDE, true>(LH_ARGS) : launch_line_cfg<LH_FMT_WIDE, false>(LH_ARGS);
+    if (entry_format == LH_FMT_P11) return final_pass ? launch_line_cfg<LH_FMT_P11, true>(LH_ARGS) : launch_line_cfg<LH_FMT_P11, false>(LH_ARGS);
+    return final_pass ? launch_line_cfg<LH_FMT_P10, true>(LH_ARGS) : launch_line_cfg<LH_FMT_P10, false>(LH_ARGS);
 #undef LH_ARGS
 }
+
+int line_entry_format(int64_t n, int64_t hmax) { return lh_entry_format(n, hmax); }
+int line_entry_bytes(int entry_format) { return entry_format == LH_FMT_WIDE ? 8 : 4; }
 
 }  // namespace sdfb200

@@ -6,10 +6,10 @@
 
 using namespace sdfb200;
 
-template <bool WIDE>
+template <int FMT>
 static void pass_lines(const int32_t* in, int32_t* out, int n, int64_t line_stride, int64_t ncols)
 {
-    typedef typename LineEntry<WIDE>::type ent_t;
+    typedef typename LineEntry<FMT>::type ent_t;
     const int nw = (n + 31) / 32;
     const int64_t tiles = (ncols + 31) / 32;
     std::vector<ent_t> stk((size_t)tiles * lh_block_entries(n), (ent_t)0x12345678);   // stale garbage: the pass must not depend on it
@@ -18,7 +18,7 @@ static void pass_lines(const int32_t* in, int32_t* out, int n, int64_t line_stri
     for (int64_t c = 0; c < ncols; c++) {
         int32_t* dst = out + c;
         const int l = (int)(c & 31);
-        line_hull_pass<WIDE>(in + c, line_stride, n, stk.data() + (c >> 5) * tile_elems + lh_lane_offset(l), pol.data() + c, ncols,
+        line_hull_pass<FMT>(in + c, line_stride, n, stk.data() + (c >> 5) * tile_elems + lh_lane_offset(l), pol.data() + c, ncols,
                              [&](int32_t m, bool neg) { *dst = neg ? -m : m; dst += line_stride; });
     }
 }
@@ -28,14 +28,16 @@ extern "C" {
 void emul_line_counters(long long* o, int reset) { for (int i = 0; i < 8; i++) { o[i] = lh_counters[i]; if (reset) lh_counters[i] = 0; } }
 
 // stk here is laid out [row][ncols] while the data is [row][line_stride]: use ncols == line_stride callers only
-int emul_line_pass(const int32_t* in, int32_t* out, int n, int64_t line_stride, int64_t ncols, int wide)
+int emul_line_pass(const int32_t* in, int32_t* out, int n, int64_t line_stride, int64_t ncols, int fmt)
 {
     if (ncols != line_stride) return -1;
-    if (wide) pass_lines<true>(in, out, n, line_stride, ncols); else pass_lines<false>(in, out, n, line_stride, ncols);
+    if (fmt == LH_FMT_WIDE) pass_lines<LH_FMT_WIDE>(in, out, n, line_stride, ncols);
+    else if (fmt == LH_FMT_P11) pass_lines<LH_FMT_P11>(in, out, n, line_stride, ncols);
+    else pass_lines<LH_FMT_P10>(in, out, n, line_stride, ncols);
     return 0;
 }
 
-int emul_line_signed_d2(const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz, int32_t* s, int wide)
+int emul_line_signed_d2(const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz, int32_t* s, int fmt)
 {
     std::vector<int32_t> t((size_t)(nx * ny * nz));
     for (int64_t l = 0; l < nx * ny; l++) {
@@ -53,10 +55,12 @@ int emul_line_signed_d2(const uint8_t* mask, int64_t nx, int64_t ny, int64_t nz,
         }
     }
     for (int64_t x = 0; x < nx; x++)
-        emul_line_pass(t.data() + x * ny * nz, s + x * ny * nz, (int)ny, nz, nz, wide);
-    emul_line_pass(s, t.data(), (int)nx, ny * nz, ny * nz, wide);
+        emul_line_pass(t.data() + x * ny * nz, s + x * ny * nz, (int)ny, nz, nz, fmt);
+    emul_line_pass(s, t.data(), (int)nx, ny * nz, ny * nz, fmt);
     for (size_t i = 0; i < t.size(); i++) s[i] = t[i];
     return 0;
 }
 
 }  // extern "C"
+
+extern "C" int emul_line_entry_format(int64_t n, int64_t hmax) { return lh_entry_format(n, hmax); }

@@ -28,6 +28,7 @@ def lib():
     u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
     L.emul_line_signed_d2.argtypes = [u8p, C.c_int64, C.c_int64, C.c_int64, i32p, C.c_int]
     L.emul_line_pass.argtypes = [i32p, i32p, C.c_int, C.c_int64, C.c_int64, C.c_int]
+    L.emul_line_entry_format.argtypes = [C.c_int64, C.c_int64]
     return L
 
 
@@ -38,7 +39,7 @@ def test_full_transform_random_grids(lib):
         p = rng.choice([0.0, 0.001, 0.01, 0.05, 0.3, 0.5, 0.9, 0.99, 1.0])
         m = (rng.random(shape) < p).astype(np.uint8)
         got = np.empty(shape, np.int32)
-        assert lib.emul_line_signed_d2(m, *shape, got, trial % 2) == 0
+        assert lib.emul_line_signed_d2(m, *shape, got, trial % 3) == 0
         assert np.array_equal(got, O.signed_d2(m)), (shape, p)
 
 
@@ -75,10 +76,10 @@ def test_line_passes_adversarial(lib):
     for trial in range(80):
         n = int(rng.choice([1, 2, 3, 31, 32, 33, 64, 65, 100, 255, 256, 511, 513, 1000, 1024, 1025, 2047, 2048]))
         ncols = int(rng.integers(1, 5))
-        for wide in (0, 1):
-            if not wide and n > 1024:
+        for wide in (0, 1, 2):                          # entry formats {pos:10,h:22}, {pos:11,h:21}, 64-bit
+            if (wide == 0 and n > 1024) or (wide == 1 and n > 2048):
                 continue
-            hmax = (3 * n * n + 2) if wide else min(3 * n * n + 2, 1 << 22)
+            hmax = (3 * n * n + 2) if wide == 2 else min(3 * n * n + 2, (1 << (22 if wide == 0 else 21)) - 1)
             lines = adversarial_lines(rng, n, ncols, hmax)
             g = np.ascontiguousarray(np.stack(lines, axis=1))
             want = np.stack([line_oracle(l) for l in lines], axis=1)
@@ -93,3 +94,13 @@ def test_structured_configs(lib, name, shape):
     got = np.empty(shape, np.int32)
     assert lib.emul_line_signed_d2(m, *shape, got, 0) == 0
     assert np.array_equal(got, O.signed_d2(m))
+
+
+def test_entry_format_choice(lib):
+    """The narrowest stack entry that holds a pass: positions < n, heights <= hmax."""
+    f = lib.emul_line_entry_format
+    assert f(1024, (1 << 22) - 2) == 0 and f(1024, (1 << 22) - 1) == 2 and f(1025, 100) == 1      # all-ones = terminator
+    assert f(2048, (1 << 21) - 2) == 1 and f(2048, (1 << 21) - 1) == 2 and f(2049, 1) == 2
+    assert f(1024, 2 * 1023 ** 2) == 0            # x pass of a 1024^3 grid
+    assert f(2048, 1023 ** 2) == 1                # y pass of 2048 x 2048 x 1024
+    assert f(2048, 1023 ** 2 + 2047 ** 2) == 2    # its x pass
