@@ -137,8 +137,8 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
     // ------------------------------------------------------------------------------------------------ build sweep
     {
         int a = 0, d = 0;                            // current run start; number of vertices on its stack
-        int bpos = -1; int32_t bY = 1 + BIG;         // left boundary site of the run (lifted height)
-        int tp = bpos; int32_t tY = bY;              // T: top of the chain
+        // left boundary site of the run: position a - 1, lifted height (a-1)^2, or 1 + BIG when there is nothing on the left
+        int tp = -1; int32_t tY = 1 + BIG;           // T: top of the chain (starts as the boundary site)
         int sp = tp; int32_t sY = tY + 1;            // S: below T, or the none-sentinel (sp == tp: the hull test is false)
         ent_t R = 0;                                 // v_{d-3} when it exists
         int ts = 0;                                  // slot a + d (next push)
@@ -152,7 +152,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 if (d >= 2) {
                     sp = E::pos(R); sY = sp * sp + E::h(R);                  // v_{d-2}
                     if (d >= 3) R = *lh_slot(stk, ts - 3);                        // v_{d-3}
-                } else if (d == 1) { sp = bpos; sY = bY; }
+                } else if (d == 1) { sp = a - 1; sY = a > 0 ? sp * sp : 1 + BIG; }
                 else { sp = tp; sY = tY + 1; }                               // T is the boundary site: nothing below
             }
         };
@@ -163,8 +163,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 pop_against(y, y * y);               // close against the right boundary site (y, 0)
                 if (d < y - a) *lh_slot(stk, ts) = E::term();
                 a = y; d = 0;
-                bpos = y - 1; bY = bpos * bpos;
-                tp = bpos; tY = bY; sp = tp; sY = tY + 1;
+                tp = y - 1; tY = tp * tp; sp = tp; sY = tY + 1;
                 ts = y;
                 prevpol = p;
             }
@@ -183,7 +182,6 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
         };
         constexpr int U = LH_U;                      // rows read ahead of the (data-dependent) stack work
         const int32_t* ip = in;
-        uint32_t* pp = pol;
         uint32_t pw = 0;
         int32_t vnx[U];
 #pragma unroll
@@ -199,7 +197,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
 #pragma unroll
             for (int u = 0; u < U; ++u) row(y0 + u, vin[u], (bits >> u) & 1u);
             pw |= bits << (y0 & 31);
-            if ((y0 & 31) == 32 - U) { *pp = pw; pp += pstride; pw = 0; }
+            if ((y0 & 31) == 32 - U) { pol[(int64_t)(y0 >> 5) * pstride] = pw; pw = 0; }
         }
         for (; y0 < n; y0 += U) {                    // the last one or two groups
             int32_t vin[U];
@@ -212,7 +210,7 @@ SDF_HD void line_hull_pass(const int32_t* __restrict__ in, int64_t stride, int n
                 row(y0 + u, vin[u], p);
                 pw |= (uint32_t)p << ((y0 + u) & 31);
             }
-            if ((y0 & 31) == 32 - U || y0 + U >= n) { *pp = pw; pp += pstride; pw = 0; }
+            if ((y0 & 31) == 32 - U || y0 + U >= n) { pol[(int64_t)(y0 >> 5) * pstride] = pw; pw = 0; }
         }
         if (d < n - a) *lh_slot(stk, ts) = E::term();  // the last run has no right boundary site
     }
