@@ -43,11 +43,16 @@ PASS_KERNEL = {"pass1_z_ms": "binary_z_kernel", "pass2_y_ms": "band_strided_kern
 
 
 def kernel_source_hash() -> str:
-    """sha256 over the CUDA sources of the build kernels: ties an ncu capture to the code it was taken from."""
+    """sha256 over the CUDA sources of the build kernels with comments and white space removed: ties an ncu capture to the
+    CODE it was taken from (editing a comment does not invalidate a measurement, editing a statement does)."""
+    import re
     h = hashlib.sha256()
     for f in ("edt_kernels.cu", "band_hull.cuh", "line_kernels.cu", "line_hull.cuh"):
-        with open(os.path.join(ROOT, "sdf_tools_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "sdf_tools_b200", "csrc", f), "r") as fh:
+            src = fh.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)          # block comments
+        src = re.sub(r"//[^\n]*", "", src)                        # line comments (no string literal in these files holds "//")
+        h.update(re.sub(r"\s+", "", src).encode())
     return h.hexdigest()[:16]
 
 

@@ -7,10 +7,10 @@
 // (Felzenszwalb / Meijster) over its whole line: a build sweep that keeps the hull of the lifted points as a stack, then a
 // query sweep that walks the stack.  No bands, no seam merges, no block-wide barriers, no shared memory.
 //
-// The stack does not fit on chip (up to n entries per line), so it lives in a global scratch field with the SAME
-// [row][line] layout as the data: the entries at depth k of 32 adjacent lines share a 128-byte row.  Adjacent lines have
-// similar hulls, so the pushes / pops / reads of a warp touch a handful of rows that stay in the (126 MB) L2; only the
-// long-lived part of a stack can spill to HBM (at most one write and one read of the final hull: <= 0.3 entries per voxel).
+// The stack does not fit on chip (up to n entries per line), so it lives in a global scratch: one block of n x 32 entries
+// per warp, laid out so that a line's own pushes, pops and fetches stay inside the 16 bytes they just touched ("Stack
+// layout" below).  Adjacent lines have similar hulls, so a warp's stack accesses land in a few cache lines that stay in
+// L1 / the 126 MB L2; only the long-lived part of a hull spills to HBM.
 //
 // Signed-fused field: s > 0 <=> voxel FREE, s = d^2 to the nearest FILLED; s < 0 <=> voxel FILLED, -s = d^2 to the
 // nearest FREE (partial over the axes done so far; |s| == SDF_INF: other polarity not seen yet).  Along a line the two
@@ -19,8 +19,8 @@
 // They are ordinary hull points: the left one is the bottom of the run's chain, the right one closes the chain (pops
 // what it hides) when the run ends.  The query sweep then needs two candidate values and one comparison per position.
 //
-// Scratch layout.  The hull of run [a,e) occupies the stack rows a, a+1, .. (at most e-a of them: one per vertex, in
-// position order), followed by a terminator when there is room; runs never share rows.  The polarity of every position
+// Scratch contents.  The hull of run [a,e) occupies the line's stack slots a, a+1, .. (at most e-a of them: one per vertex,
+// in position order), followed by a terminator when there is room; runs never share slots.  The polarity of every position
 // goes to a bit field pol[word][line] (1/32 of the field), which the query sweep reads to find run ends and signs.
 //
 // Exactness: all integer; hull tests are cross-multiplied in int64 (|dY| < 2^25, |dq| < 2^11).

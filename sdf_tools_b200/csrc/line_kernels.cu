@@ -3,9 +3,9 @@
 // the layout.  Replaces the per-axis loops of sdf_generation::BuildDistanceField
 // (/root/reference/include/sdf_tools/sdf_generation.hpp:95-207) and, in the last pass, the combine loop (:246-268).
 //
-// Threads are numbered along the contiguous direction (lid = outer * ncols + col), so a warp reads, pushes and writes
-// 128-byte rows.  Out of place: in -> out (the stack must not be clobbered by the results), every voxel is read once and
-// written once; stack traffic stays in L2 except for the long-lived part of a hull.
+// Threads are numbered along the contiguous direction (lid = outer * ncols + col), so a warp reads and writes 128-byte
+// rows of the field.  Out of place (in -> out: the axes may be re-ordered on the way), every voxel is read once and
+// written once; the stack traffic stays in L1 / L2 except for the long-lived part of a hull.
 #include "edt_kernels.cuh"
 #include "line_hull.cuh"
 
