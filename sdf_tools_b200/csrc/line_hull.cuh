@@ -23,7 +23,8 @@
 // in position order), followed by a terminator when there is room; runs never share slots.  The polarity of every position
 // goes to a bit field pol[word][line] (1/32 of the field), which the query sweep reads to find run ends and signs.
 //
-// Exactness: all integer; hull tests are cross-multiplied in int64 (|dY| < 2^25, |dq| < 2^11).
+// Exactness: all integer; hull tests are cross-multiplied in int64 (|dY| <= 2^30 + 2^25 with the "nothing on the left"
+// site, |dq| < 2^11).
 #pragma once
 #include <stdint.h>
 
@@ -85,7 +86,7 @@ SDF_HD int lh_entry_format(int64_t n, int64_t hmax)
 // hull fetches of the query sweep walk a lane's slots in order), instead of sharing every sector with seven other lines
 // that want it at different times, as the plain [slot][line] layout does.  Measured at 1024^3 (y / x pass, ms):
 // C = 1: 4.36 / 7.77, C = 2: 4.20 / 7.12, C = 4: 4.08 / 6.87, C = 8: 4.14 / 7.05, C = 16: 4.24 / 7.25; DRAM traffic of the
-// x pass 2.07 -> 1.5 x the algorithmic bytes, L1 hit rate 68 -> 81 %.  `stk` below is the lane's slot 0: block base + l * C.
+// x pass 2.07 -> 1.63 x the algorithmic bytes, L1 hit rate 68 -> 81 %.  `stk` below is the lane's slot 0: block base + l * C.
 #ifndef LH_U
 #define LH_U 4
 #endif
