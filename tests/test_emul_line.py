@@ -104,3 +104,37 @@ def test_entry_format_choice(lib):
     assert f(1024, 2 * 1023 ** 2) == 0            # x pass of a 1024^3 grid
     assert f(2048, 1023 ** 2) == 1                # y pass of 2048 x 2048 x 1024
     assert f(2048, 1023 ** 2 + 2047 ** 2) == 2    # its x pass
+
+
+def test_paths_are_exercised(lib):
+    """The adversarial lines must actually reach the data-dependent paths of the sweeps: pops (incl. chains long enough to
+    reload the third chain element from the stack), run changes, query advances -- and agree with the banded kernel's
+    emulator on the same lines (two independent implementations of the same pass)."""
+    import test_emul_band as TB
+    L = C.CDLL(LIB)
+    L.emul_line_counters.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    ctr = (C.c_longlong * 8)()
+    L.emul_line_counters(ctr, 1)
+    rng = np.random.default_rng(23)
+    n, ncols = 700, 6
+    lines = adversarial_lines(rng, n, ncols, 1 << 21)
+    # a staircase that ends in a deep pit: the pit pops hundreds of vertices in one chain
+    h = (np.arange(n)[::-1] // 2 + 5) ** 2
+    h[-1] = 1
+    lines[0] = h.astype(np.int32)
+    g = np.ascontiguousarray(np.stack(lines, axis=1))
+    want = np.stack([line_oracle(l) for l in lines], axis=1)
+    got = np.empty_like(g)
+    assert lib.emul_line_pass(g, got, n, ncols, ncols, 0) == 0
+    assert np.array_equal(got, want)
+    L.emul_line_counters(ctr, 0)
+    sites, finite, pops, runs, adv = ctr[0], ctr[1], ctr[2], ctr[3], ctr[4]
+    assert sites == n * ncols and 0 < finite <= sites and pops > 300 and adv > 0, list(ctr)
+    # the banded emulator on the same lines (in place)
+    if os.path.exists(TB.LIB):
+        B = C.CDLL(TB.LIB)
+        i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+        B.emul_band_pass.argtypes = [i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64]
+        gb = g.copy()
+        assert B.emul_band_pass(gb, n, ncols, ncols, 5, 16, 0, 1) == 0
+        assert np.array_equal(gb, got)
